@@ -1,0 +1,75 @@
+// Shared declarations for the marf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/marf_b200.h"
+
+namespace marf {
+
+constexpr int kMaxBands = 16;          // posenc bands supported (arch.posenc.L_2D <= 16)
+
+// ---------------------------------------------------------------------------------------------
+// Geometry constants of one handle (warp.py:9-21) + encoding schedule, passed by value to kernels.
+struct Geo {
+  int H, W;                // canvas
+  int h, w;                // patch grid actually traversed (patch_H x patch_W when cropped, else H x W)
+  int y0, x0;              // crop origin (0 when not cropped)
+  int rows, row_offset;    // local row shard of each patch
+  int patch_offset;        // global index of local patch 0
+  float norm_h, norm_w;    // H/max(H,W), W/max(H,W)
+  int L;                   // posenc bands
+  int d_in;                // 2 + 4L (or 2)
+  float band_w[kMaxBands]; // c2f weights w_k (1 when c2f is off)
+  float band_f[kMaxBands]; // f32(2^k * pi)
+};
+
+// normalized pixel coordinate of (row r, col c) of the traversed grid — same f32 op order as
+// warp.py:38-49: ((i + 0.5) / n * 2 - 1) * norm
+__device__ __forceinline__ void grid_xy(const Geo& g, int r, int c, float& x, float& y) {
+  float fy = (float)(r + g.y0) + 0.5f;
+  float fx = (float)(c + g.x0) + 0.5f;
+  y = (__fdiv_rn(fy, (float)g.H) * 2.0f - 1.0f) * g.norm_h;
+  x = (__fdiv_rn(fx, (float)g.W) * 2.0f - 1.0f) * g.norm_w;
+}
+
+// homography apply, warp.py:74-78: q = [x,y,1] H^T ; (u,v) = q_xy / (q_z + 1e-8)
+__device__ __forceinline__ void apply_h(const float* __restrict__ Hm, float x, float y, float& u, float& v, float& qz) {
+  float q0 = Hm[0] * x + Hm[1] * y + Hm[2];
+  float q1 = Hm[3] * x + Hm[4] * y + Hm[5];
+  float q2 = Hm[6] * x + Hm[7] * y + Hm[8];
+  qz = q2 + 1e-8f;
+  u = __fdiv_rn(q0, qz);
+  v = __fdiv_rn(q1, qz);
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+inline int pad4(int a) { return (a + 3) / 4 * 4; }
+
+// loss coefficients resolved on device from the (possibly all-reduced) sums: no host sync.
+struct LossCoef {
+  double inv_n_rgb;    // 1 / N_RGB
+  double s_over_n2;    // 3 * S_RGB / N_RGB^2        (d rgb_loss / d m, constant part)
+  double inv_n_mask;   // 1 / N_MASK
+  double inv_n_edge;   // 1 / N_EDGE  (0 when no edge term)
+  double se_over_n2;   // 3 * S_EDGE / N_EDGE^2
+};
+
+}  // namespace marf

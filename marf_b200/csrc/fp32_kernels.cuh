@@ -1,0 +1,650 @@
+// fp32 (CUDA-core) kernels of the planar step: geometry, encodings, SGEMM family, losses.
+// This is the parity mode (MARF_FP32): every arithmetic step is fp32 like the reference's
+// eager PyTorch path, reductions are fp64.
+#pragma once
+#include "common.cuh"
+
+namespace marf {
+
+// ============================================================================================
+// sl(3) -> SL(3): H = expm(A(h))  (warp.py:98-106), and its adjoint for the backward pass
+// (SURVEY.md §8 a-3): dA = expm([[A^T, G],[0, A^T]])[:3,3:].  One thread per patch, fp64 inside.
+// ============================================================================================
+template <int N>
+__device__ void expm_small(const double* A, double* E) {
+  double nrm = 0.0;
+  for (int j = 0; j < N; ++j) {
+    double s = 0.0;
+    for (int i = 0; i < N; ++i) s += fabs(A[i * N + j]);
+    nrm = fmax(nrm, s);
+  }
+  int sq = 0;
+  while (nrm > 0.25 && sq < 60) { nrm *= 0.5; ++sq; }
+  double scale = ldexp(1.0, -sq);
+  double X[N * N], T[N * N], R[N * N];
+  for (int i = 0; i < N * N; ++i) { X[i] = A[i] * scale; T[i] = (i / N == i % N) ? 1.0 : 0.0; R[i] = T[i]; }
+  for (int k = 1; k <= 16; ++k) {            // Taylor: 0.25^17/17! < 1e-24
+    double Tn[N * N];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double s = 0.0;
+        for (int q = 0; q < N; ++q) s += T[i * N + q] * X[q * N + j];
+        Tn[i * N + j] = s / (double)k;
+      }
+    for (int i = 0; i < N * N; ++i) { T[i] = Tn[i]; R[i] += Tn[i]; }
+  }
+  for (int s = 0; s < sq; ++s) {
+    double Rn[N * N];
+    for (int i = 0; i < N; ++i)
+      for (int j = 0; j < N; ++j) {
+        double acc = 0.0;
+        for (int q = 0; q < N; ++q) acc += R[i * N + q] * R[q * N + j];
+        Rn[i * N + j] = acc;
+      }
+    for (int i = 0; i < N * N; ++i) R[i] = Rn[i];
+  }
+  for (int i = 0; i < N * N; ++i) E[i] = R[i];
+}
+
+__device__ __forceinline__ void sl3_generator(const float* h, double* A) {
+  // A = [[h5,h3,h1],[h4,-h5-h6,h2],[h7,h8,h6]], h1..h8 = h[0..7]  (warp.py:100-104)
+  A[0] = h[4]; A[1] = h[2]; A[2] = h[0];
+  A[3] = h[3]; A[4] = -(double)h[4] - (double)h[5]; A[5] = h[1];
+  A[6] = h[6]; A[7] = h[7]; A[8] = h[5];
+}
+
+__global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  double A[9], E[9];
+  if (warp) sl3_generator(warp + 8 * b, A);
+  else for (int i = 0; i < 9; ++i) A[i] = 0.0;
+  expm_small<3>(A, E);
+  for (int i = 0; i < 9; ++i) out9[9 * b + i] = (float)E[i];
+}
+
+// G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches)
+__global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
+                               int n_local, float* __restrict__ g_warp) {
+  int bl = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bl >= n_local) return;
+  int b = bl + patch_offset;
+  double A[9], M[36], E[36];
+  sl3_generator(warp + 8 * b, A);
+  for (int i = 0; i < 36; ++i) M[i] = 0.0;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      M[i * 6 + j] = A[j * 3 + i];                 // A^T
+      M[(i + 3) * 6 + (j + 3)] = A[j * 3 + i];     // A^T
+      M[i * 6 + (j + 3)] = G[9 * bl + i * 3 + j];  // upstream
+    }
+  expm_small<6>(M, E);
+  double dA[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) dA[i * 3 + j] = E[i * 6 + (j + 3)];
+  float* o = g_warp + 8 * b;
+  o[0] = (float)dA[2];            // h1 -> A02
+  o[1] = (float)dA[5];            // h2 -> A12
+  o[2] = (float)dA[1];            // h3 -> A01
+  o[3] = (float)dA[3];            // h4 -> A10
+  o[4] = (float)(dA[0] - dA[4]);  // h5 -> A00, -A11
+  o[5] = (float)(dA[8] - dA[4]);  // h6 -> A22, -A11
+  o[6] = (float)dA[6];            // h7 -> A20
+  o[7] = (float)dA[7];            // h8 -> A21
+}
+
+// warped crop corners (warp.py:83-93): [(X0,Y0),(X0,Y1),(X1,Y1),(X1,Y0)]
+__global__ void k_warp_corners(Geo g, const float* __restrict__ Hm, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 4) return;
+  int b = i / 4, c = i % 4;
+  // python doubles rounded to f32 once (torch.tensor(corners, dtype=float32))
+  double Y[2], X[2];
+  int yc[2] = {g.H / 2 - g.h / 2, g.H / 2 + g.h / 2};
+  int xc[2] = {g.W / 2 - g.w / 2, g.W / 2 + g.w / 2};
+  double nh = (double)g.H / (double)max(g.H, g.W), nw = (double)g.W / (double)max(g.H, g.W);
+  for (int k = 0; k < 2; ++k) {
+    Y[k] = ((yc[k] + 0.5) / g.H * 2 - 1) * nh;
+    X[k] = ((xc[k] + 0.5) / g.W * 2 - 1) * nw;
+  }
+  const int xi[4] = {0, 0, 1, 1}, yi[4] = {0, 1, 1, 0};
+  float x = (float)X[xi[c]], y = (float)Y[yi[c]], u, v, qz;
+  apply_h(Hm + 9 * b, x, y, u, v, qz);
+  out[2 * i] = u;
+  out[2 * i + 1] = v;
+}
+
+// ============================================================================================
+// encoding prologue: grid -> warp -> [u, v, w_k sin(f_k u), w_k cos(f_k u), w_k sin(f_k v), w_k cos(f_k v)]
+// (warp.py:33-81, model/planar.py:451-471,434).  One thread per pixel-sample; X0 is [n_pad, ld].
+// ============================================================================================
+struct PxRange {
+  long long first;   // first local pixel-sample of the chunk (index into batch*rows*w)
+  int count;         // valid pixel-samples in the chunk
+  int padded;        // rows allocated (multiple of 128); rows >= count are written as zeros
+};
+
+__device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int& r, int& c) {
+  long long per = (long long)g.rows * g.w;
+  b = (int)(i / per);
+  int rem = (int)(i - (long long)b * per);
+  r = rem / g.w + g.row_offset;
+  c = rem - (rem / g.w) * g.w;
+}
+
+__global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [batch_global,9] or identity */,
+                         int identity, float* __restrict__ X0, int ld) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rg.padded) return;
+  float* o = X0 + (size_t)t * ld;
+  if (t >= rg.count) {
+    for (int j = 0; j < ld; ++j) o[j] = 0.0f;
+    return;
+  }
+  int b, r, c;
+  decode_px(g, rg.first + t, b, r, c);
+  float x, y, u, v, qz;
+  grid_xy(g, r, c, x, y);
+  if (identity) { u = x; v = y; }
+  else apply_h(Hm + 9 * (b + g.patch_offset), x, y, u, v, qz);
+  o[0] = u;
+  o[1] = v;
+  const int L = g.L;
+  for (int k = 0; k < L; ++k) {
+    float su, cu, sv, cv;
+    sincosf(u * g.band_f[k], &su, &cu);
+    sincosf(v * g.band_f[k], &sv, &cv);
+    float wk = g.band_w[k];
+    o[2 + k] = su * wk;
+    o[2 + L + k] = cu * wk;
+    o[2 + 2 * L + k] = sv * wk;
+    o[2 + 3 * L + k] = cv * wk;
+  }
+  for (int j = g.d_in; j < ld; ++j) o[j] = 0.0f;
+}
+
+// backward of the prologue: dX0 [n,ld] -> per-patch G = sum_p dq (x) [x,y,1]  (SURVEY.md §8 a-4,a-5)
+__global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ Hm, const float* __restrict__ dX0,
+                                  int ld, double* __restrict__ G /* [batch,9] local patches */) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = t < rg.count;
+  int b = -1, r = 0, c = 0;
+  float acc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) acc[i] = 0.0f;
+  if (valid) {
+    decode_px(g, rg.first + t, b, r, c);
+    float x, y, u, v, qz;
+    grid_xy(g, r, c, x, y);
+    apply_h(Hm + 9 * (b + g.patch_offset), x, y, u, v, qz);
+    const float* d = dX0 + (size_t)t * ld;
+    float gu = d[0], gv = d[1];
+    const int L = g.L;
+    for (int k = 0; k < L; ++k) {
+      float su, cu, sv, cv;
+      float f = g.band_f[k];
+      sincosf(u * f, &su, &cu);
+      sincosf(v * f, &sv, &cv);
+      float wf = g.band_w[k] * f;
+      gu += wf * (d[2 + k] * cu - d[2 + L + k] * su);
+      gv += wf * (d[2 + 2 * L + k] * cv - d[2 + 3 * L + k] * sv);
+    }
+    float inv = 1.0f / qz;
+    float dq0 = gu * inv, dq1 = gv * inv, dq2 = -(gu * u + gv * v) * inv;
+    acc[0] = dq0 * x; acc[1] = dq0 * y; acc[2] = dq0;
+    acc[3] = dq1 * x; acc[4] = dq1 * y; acc[5] = dq1;
+    acc[6] = dq2 * x; acc[7] = dq2 * y; acc[8] = dq2;
+  }
+  int b0 = __shfl_sync(0xffffffffu, b, 0);
+  bool uniform = __all_sync(0xffffffffu, b == b0);
+  if (uniform) {
+    if (b0 < 0) return;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      float s = warp_sum(acc[i]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&G[9 * b0 + i], (double)s);
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) atomicAdd(&G[9 * b + i], (double)acc[i]);
+  }
+}
+
+// ============================================================================================
+// mask-head input features (model/planar.py:342-349, :491-518): [E[trunc r], E[trunc g], E[trunc b], PosEmbedding(xy)]
+// one block of 128 threads per pixel-sample row; iteration-invariant (cached by the engine when possible).
+// ============================================================================================
+__global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
+                                int embed_dim, int n_freqs, float* __restrict__ F, int ld) {
+  int t = blockIdx.x;
+  float* o = F + (size_t)t * ld;
+  if (t >= rg.count) {
+    for (int j = threadIdx.x; j < ld; j += blockDim.x) o[j] = 0.0f;
+    return;
+  }
+  int b, r, c;
+  long long i = rg.first + t;
+  decode_px(g, i, b, r, c);
+  long long per = (long long)g.rows * g.w;
+  long long rem = i - (long long)b * per;
+  int k_col = 3 * embed_dim;
+  for (int j = threadIdx.x; j < k_col; j += blockDim.x) {
+    int ch = j / embed_dim, e = j - ch * embed_dim;
+    float val = rgb[((long long)b * 3 + ch) * per + rem];
+    long long idx = (long long)val;                 // .long(): truncation toward zero
+    o[j] = embed[idx * embed_dim + e];
+  }
+  float x, y;
+  grid_xy(g, r, c, x, y);
+  int k_uv = 2 + 4 * n_freqs;
+  for (int j = threadIdx.x; j < k_uv; j += blockDim.x) {
+    float val;
+    if (j < 2) val = j == 0 ? x : y;
+    else {
+      int q = j - 2, fi = q / 4, w4 = q % 4;        // per frequency: sin x, sin y, cos x, cos y
+      float f = (float)(1 << fi);
+      float a = f * ((w4 & 1) ? y : x);
+      val = (w4 < 2) ? sinf(a) : cosf(a);
+    }
+    o[k_col + j] = val;
+  }
+  for (int j = k_col + k_uv + threadIdx.x; j < ld; j += blockDim.x) o[j] = 0.0f;
+}
+
+// ============================================================================================
+// SGEMM family.  C[M,N] (+)= A[M,K] * B[K,N] with fp32 FMA, 128 x (16*TN) x 16 tiles, 256 threads.
+//   A_KC: A(m,k) = A[m*lda + k]  (K contiguous)      else A(m,k) = A[k*lda + m]  (M contiguous)
+//   B_KC: B(k,n) = B[n*ldb + k]  (K contiguous)      else B(k,n) = B[k*ldb + n]  (N contiguous)
+// All of M,N,K,lda,ldb,ldc are multiples of 4 (engine pads), pointers 16-byte aligned.
+// ============================================================================================
+enum Epi { EPI_BIAS = 0, EPI_BIAS_RELU = 1, EPI_PLAIN = 2, EPI_RELU_MASK = 3, EPI_ATOMIC = 4, EPI_ATOMIC_T = 5 };
+
+constexpr int GBM = 128, GBK = 16;
+
+__device__ __forceinline__ int swz(int k, int idx) { return idx ^ (((k >> 2) & 3) << 3); }
+
+template <bool KC, int ROWS>
+__device__ __forceinline__ void load_tile(float (*S)[GBM], const float* __restrict__ P, int ld, int row0, int nrows,
+                                          int k0, int kend, int tid) {
+  // fills S[k][row] for row in [0,ROWS), k in [0,GBK); zero outside [row0+.. < nrows) x [k0+.. < kend)
+  if (KC) {
+    // float4 along K: ROWS*4 float4 in the tile
+    for (int idx = tid; idx < ROWS * (GBK / 4); idx += 256) {
+      int row = idx >> 2, kq = (idx & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      int gr = row0 + row, gk = k0 + kq;
+      if (gr < nrows && gk < kend) v = *reinterpret_cast<const float4*>(P + (size_t)gr * ld + gk);
+      S[kq + 0][swz(kq + 0, row)] = v.x;
+      S[kq + 1][swz(kq + 1, row)] = v.y;
+      S[kq + 2][swz(kq + 2, row)] = v.z;
+      S[kq + 3][swz(kq + 3, row)] = v.w;
+    }
+  } else {
+    // float4 along the row index: GBK * ROWS/4 float4
+    for (int idx = tid; idx < GBK * (ROWS / 4); idx += 256) {
+      int k = idx / (ROWS / 4), r4 = (idx - k * (ROWS / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      int gr = row0 + r4, gk = k0 + k;
+      if (gr < nrows && gk < kend) v = *reinterpret_cast<const float4*>(P + (size_t)gk * ld + gr);
+      *reinterpret_cast<float4*>(&S[k][swz(k, r4)]) = v;
+    }
+  }
+}
+
+template <bool A_KC, bool B_KC, int TN, int EPI>
+__global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+                                               const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                               const float* __restrict__ aux, int ldaux, int k_split) {
+  constexpr int BN = 16 * TN;
+  __shared__ __align__(16) float As[2][GBK][GBM];
+  __shared__ __align__(16) float Bs[2][GBK][GBM];   // only the first BN columns are used
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * GBM, n0 = blockIdx.y * BN;
+  // split-K range (multiples of GBK)
+  int kt_total = (K + GBK - 1) / GBK;
+  int kt_per = (kt_total + k_split - 1) / k_split;
+  int kt_begin = blockIdx.z * kt_per;
+  int kt_end = min(kt_total, kt_begin + kt_per);
+  if (kt_begin >= kt_end) return;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tile<A_KC, GBM>(As[0], A, lda, m0, M, kt_begin * GBK, K, tid);
+  load_tile<B_KC, BN>(Bs[0], B, ldb, n0, N, kt_begin * GBK, K, tid);
+  __syncthreads();
+  int buf = 0;
+  for (int kt = kt_begin; kt < kt_end; ++kt) {
+    if (kt + 1 < kt_end) {
+      load_tile<A_KC, GBM>(As[buf ^ 1], A, lda, m0, M, (kt + 1) * GBK, K, tid);
+      load_tile<B_KC, BN>(Bs[buf ^ 1], B, ldb, n0, N, (kt + 1) * GBK, K, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < GBK; ++k) {
+      float a[8], b[TN];
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][swz(k, ty * 4)]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][swz(k, 64 + ty * 4)]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      if (TN == 8) {
+        float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][swz(k, tx * 4)]);
+        float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][swz(k, 64 + tx * 4)]);
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+        b[4 % TN] = b1.x; b[5 % TN] = b1.y; b[6 % TN] = b1.z; b[7 % TN] = b1.w;
+      } else {
+        b[0] = Bs[buf][k][swz(k, tx)];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+
+  // epilogue
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + (TN == 8 ? (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)) : tx);
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (EPI == EPI_BIAS) C[(size_t)m * ldc + n] = v + aux[n];
+      else if (EPI == EPI_BIAS_RELU) C[(size_t)m * ldc + n] = fmaxf(v + aux[n], 0.f);
+      else if (EPI == EPI_PLAIN) C[(size_t)m * ldc + n] = v;
+      else if (EPI == EPI_RELU_MASK) C[(size_t)m * ldc + n] = aux[(size_t)m * ldaux + n] > 0.f ? v : 0.f;
+      else if (EPI == EPI_ATOMIC) atomicAdd(&C[(size_t)m * ldc + n], v);
+      else atomicAdd(&C[(size_t)n * ldc + m], v);   // transposed accumulate
+    }
+  }
+}
+
+// db[j] += sum_m dY[m,j]
+__global__ void k_colsum(int M, int N, const float* __restrict__ dY, int ld, float* __restrict__ db, int rows_per_block) {
+  __shared__ float red[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int n = blockIdx.x * 32 + tx;
+  int mb = blockIdx.y * rows_per_block, me = min(M, mb + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int m = mb + ty; m < me; m += 8) s += dY[(size_t)m * ld + n];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i][tx];
+    atomicAdd(&db[n], tot);
+  }
+}
+
+// weight (un)packing between torch layouts and the padded workspace
+__global__ void k_pack(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp, int prow, int pcol) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= prow * pcol) return;
+  int r = i / pcol, c = i - r * pcol;
+  Wp[i] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f;
+}
+__global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* __restrict__ W, int rows, int cols) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  int r = i / cols, c = i - r * cols;
+  W[i] = Wp[(size_t)r * pcol + c];
+}
+// copy `cols` columns between row-major buffers (skip-connection concat / split)
+__global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int lds, int soff, float* __restrict__ dst,
+                            int ldd, int doff, int accumulate) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * cols) return;
+  int m = (int)(i / cols), c = (int)(i - (long long)m * cols);
+  float v = src[(size_t)m * lds + soff + c];
+  float* d = dst + (size_t)m * ldd + doff + c;
+  *d = accumulate ? *d + v : v;
+}
+// dY_prev[m,j] = dX[m,j] * (act[m,j] > 0) for j < cols
+__global__ void k_relu_mask(int M, int cols, const float* __restrict__ dX, int ldx, const float* __restrict__ act,
+                            int lda, float* __restrict__ dY, int ldy) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * cols) return;
+  int m = (int)(i / cols), c = (int)(i - (long long)m * cols);
+  dY[(size_t)m * ldy + c] = act[(size_t)m * lda + c] > 0.f ? dX[(size_t)m * ldx + c] : 0.f;
+}
+
+// ============================================================================================
+// losses (model/planar.py:355-391) — statistics pass and gradient pass
+// ============================================================================================
+struct LossArgs {
+  int mask_mode;               // marf_mask_mode
+  const float* logits; int ld; // image MLP output before sigmoid [n, ld]
+  const float* mlogits; int mld; // mask head output before sigmoid [n, mld] (implicit only)
+  const float* rgb;            // [batch,3,rows,w]
+  const float* masks;          // [batch,1,rows,w] (disk only)
+  float* rgb_pred;             // optional [n_total,3]
+  float* mask_pred;            // optional [n_total]
+};
+
+__global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__ sums) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double s_rgb = 0, n_rgb = 0, s_mask = 0, n_mask = 0, bad = 0;
+  if (t < rg.count) {
+    long long i = rg.first + t;
+    long long per = (long long)g.rows * g.w;
+    long long b = i / per, rem = i - b * per;
+    float m = 1.f;
+    if (a.mask_mode == MARF_MASK_DISK) m = a.masks[i];
+    else if (a.mask_mode == MARF_MASK_IMPLICIT) {
+      m = sigmoidf_acc(a.mlogits[(size_t)t * a.mld]);
+      if (a.mask_pred) a.mask_pred[i] = m;
+      float om = 1.f - m;
+      s_mask = (double)(om * om);
+    }
+    n_mask = 1.0;
+    float acc = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float p = sigmoidf_acc(a.logits[(size_t)t * a.ld + c]);
+      if (a.rgb_pred) a.rgb_pred[i * 3 + c] = p;
+      float d = (p - a.rgb[(b * 3 + c) * per + rem]) * m;
+      acc += d * d;
+      if (!isfinite(p)) bad = 1.0;
+    }
+    s_rgb = (double)acc;
+    n_rgb = 3.0 * (double)m;
+  }
+  s_rgb = warp_sum(s_rgb); n_rgb = warp_sum(n_rgb); s_mask = warp_sum(s_mask); n_mask = warp_sum(n_mask);
+  bad = warp_sum(bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[MARF_S_RGB], s_rgb);
+    atomicAdd(&sums[MARF_N_RGB], n_rgb);
+    if (a.mask_mode == MARF_MASK_IMPLICIT) {
+      atomicAdd(&sums[MARF_S_MASK], s_mask);
+      atomicAdd(&sums[MARF_N_MASK], n_mask);
+    }
+    if (bad != 0.0) atomicAdd(&sums[MARF_NONFINITE], bad);
+  }
+}
+
+// static mask sum (disk masks): N_RGB = 3 * sum m over the local shard
+__global__ void k_sum_f32(const float* __restrict__ x, long long n, double scale, double* __restrict__ out) {
+  double s = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += (double)x[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+}
+
+// edge-loss statistics: S_EDGE = sum_c ((e_c - l) m)^2, N_EDGE = 3 sum m   (model/planar.py:366-369)
+struct EdgeArgs {
+  int mask_mode;
+  const double* edge_pred;     // [batch,3,rows,w]
+  const double* edge_label;    // [batch,lc,rows,w]
+  int label_channels;
+  const float* masks_eroded;   // disk mode
+  const float* mask_pred;      // implicit mode [n_total]
+};
+__global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __restrict__ sums) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0, nn = 0;
+  if (i < n_total) {
+    long long per = (long long)g.rows * g.w;
+    long long b = i / per, rem = i - b * per;
+    double m = 1.0;
+    if (a.mask_mode == MARF_MASK_DISK) m = (double)a.masks_eroded[i];
+    else if (a.mask_mode == MARF_MASK_IMPLICIT) m = (double)a.mask_pred[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double l = a.edge_label[(b * a.label_channels + (a.label_channels == 1 ? 0 : c)) * per + rem];
+      double d = (a.edge_pred[(b * 3 + c) * per + rem] - l) * m;
+      s += d * d;
+    }
+    nn = 3.0 * m;
+  }
+  s = warp_sum(s); nn = warp_sum(nn);
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[MARF_S_EDGE], s); atomicAdd(&sums[MARF_N_EDGE], nn); }
+}
+
+// resolve normalisers on device (after an optional all-reduce of `sums`): no host round trip
+__global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
+                            int use_edges, LossCoef* __restrict__ out) {
+  double n_rgb = norm_rgb_host > 0 ? norm_rgb_host : sums[MARF_N_RGB];
+  double n_edge = norm_edge_host > 0 ? norm_edge_host : sums[MARF_N_EDGE];
+  LossCoef c;
+  c.inv_n_rgb = 1.0 / n_rgb;
+  c.s_over_n2 = 3.0 * sums[MARF_S_RGB] / (n_rgb * n_rgb);
+  c.inv_n_mask = sums[MARF_N_MASK] > 0 ? 1.0 / sums[MARF_N_MASK] : 0.0;
+  c.inv_n_edge = (use_edges && n_edge > 0) ? 1.0 / n_edge : 0.0;
+  c.se_over_n2 = (use_edges && n_edge > 0) ? 3.0 * sums[MARF_S_EDGE] / (n_edge * n_edge) : 0.0;
+  *out = c;
+}
+
+struct GradArgs {
+  LossArgs l;
+  float c_rgb, c_mask, c_edge;
+  const double* edge_pred;     // implicit + edges: per-pixel edge residual feeds the mask gradient
+  const double* edge_label;
+  int label_channels;
+  float* dlogits; int dld;     // out [n_pad, dld]
+  float* dmlogits; int dmld;   // out [n_pad, dmld] (implicit only)
+};
+
+__global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rg.padded) return;
+  float* dl = a.dlogits + (size_t)t * a.dld;
+  float* dm = a.dmlogits ? a.dmlogits + (size_t)t * a.dmld : nullptr;
+  if (t >= rg.count) {
+    for (int j = 0; j < a.dld; ++j) dl[j] = 0.f;
+    if (dm) for (int j = 0; j < a.dmld; ++j) dm[j] = 0.f;
+    return;
+  }
+  const LossCoef cf = *coefp;
+  long long i = rg.first + t;
+  long long per = (long long)g.rows * g.w;
+  long long b = i / per, rem = i - b * per;
+  float m = 1.f;
+  if (a.l.mask_mode == MARF_MASK_DISK) m = a.l.masks[i];
+  else if (a.l.mask_mode == MARF_MASK_IMPLICIT) m = sigmoidf_acc(a.l.mlogits[(size_t)t * a.l.mld]);
+  float k_rgb = (float)(2.0 * (double)a.c_rgb * cf.inv_n_rgb);
+  float sum_d2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float p = sigmoidf_acc(a.l.logits[(size_t)t * a.l.ld + c]);
+    float d = p - a.l.rgb[(b * 3 + c) * per + rem];
+    sum_d2 += d * d;
+    dl[c] = k_rgb * d * m * m * p * (1.f - p);
+  }
+  for (int j = 3; j < a.dld; ++j) dl[j] = 0.f;
+  if (dm) {
+    // d all / d m_p  
+    double gm = (double)a.c_rgb * (2.0 * m * sum_d2 * cf.inv_n_rgb - cf.s_over_n2)
+              + (double)a.c_mask * (-2.0 * (1.0 - m) * cf.inv_n_mask);
+    if (a.edge_pred) {
+      double e2 = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double l = a.edge_label[(b * a.label_channels + (a.label_channels == 1 ? 0 : c)) * per + rem];
+        double e = a.edge_pred[(b * 3 + c) * per + rem] - l;
+        e2 += e * e;
+      }
+      gm += (double)a.c_edge * (2.0 * m * e2 * cf.inv_n_edge - cf.se_over_n2);
+    }
+    dm[0] = (float)(gm * (double)(m * (1.f - m)));
+    for (int j = 1; j < a.dmld; ++j) dm[j] = 0.f;
+  }
+}
+
+// plain sigmoid of the first 3 columns (render path)
+__global__ void k_sigmoid_out(int n, const float* __restrict__ logits, int ld, float* __restrict__ out) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) out[(size_t)t * 3 + c] = sigmoidf_acc(logits[(size_t)t * ld + c]);
+}
+
+// ============================================================================================
+// edge branch (inputs.py:50-69): Sobel-3 x/y in fp64 -> magnitude -> 5x5 Gaussian (sigma=0 -> [1 4 6 4 1]/16),
+// OpenCV default border BORDER_REFLECT_101.  Image layouts: planar [n,c,rows,w] or interleaved [n,rows*w,c].
+// ============================================================================================
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+__global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int rows, int w, int interleaved,
+                            double* __restrict__ mag /* planar [n,ch,rows,w] */) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)n * ch * rows * w;
+  if (i >= total) return;
+  int x = (int)(i % w);
+  int y = (int)((i / w) % rows);
+  int c = (int)((i / ((long long)w * rows)) % ch);
+  int b = (int)(i / ((long long)w * rows * ch));
+  auto px = [&](int yy, int xx) -> double {
+    yy = reflect101(yy, rows); xx = reflect101(xx, w);
+    return interleaved ? (double)img[(((long long)b * rows + yy) * w + xx) * ch + c]
+                       : (double)img[(((long long)b * ch + c) * rows + yy) * w + xx];
+  };
+  double gx = 0, gy = 0;
+  const double s[3] = {1, 2, 1}, d[3] = {-1, 0, 1};
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      double v = px(y + dy - 1, x + dx - 1);
+      gx += s[dy] * d[dx] * v;
+      gy += d[dy] * s[dx] * v;
+    }
+  mag[i] = sqrt(gx * gx + gy * gy);
+}
+
+__global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)planes * rows * w;
+  if (i >= total) return;
+  int x = (int)(i % w);
+  int y = (int)((i / w) % rows);
+  long long p = i / ((long long)w * rows);
+  const double g5[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
+  const double* pl = mag + p * rows * w;
+  // separable, rows first then columns (same result as OpenCV's row/column filter order up to fp64 rounding)
+  double acc = 0;
+#pragma unroll
+  for (int dy = 0; dy < 5; ++dy) {
+    int yy = reflect101(y + dy - 2, rows);
+    double rowacc = 0;
+#pragma unroll
+    for (int dx = 0; dx < 5; ++dx) rowacc += g5[dx] * pl[(long long)yy * w + reflect101(x + dx - 2, w)];
+    acc += g5[dy] * rowacc;
+  }
+  out[i] = acc;
+}
+
+}  // namespace marf
