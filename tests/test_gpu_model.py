@@ -1,0 +1,99 @@
+"""GPU: the reference-facing plugin (Model / Graph) end to end — seed-matched init, train_iteration semantics
+(Adam, fix_first, progress and alpha schedules) against the trajectory recorded from the unmodified reference."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import fixtures as fx
+import planar_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(tmp_path, **over):
+    from marf_b200.attrdict import AttrDict
+    from marf_b200 import options
+    opt = options.load_options("options/planar.yaml")
+    opt.update(model="planar", yaml="planar", output_path=str(tmp_path), device="cuda:0", tb=None,
+               use_homographies=False, world_size=1, rank=0)
+    for k, v in over.items():
+        if isinstance(v, dict):
+            opt[k].update(v)
+        else:
+            opt[k] = v
+    return opt
+
+
+class _Loader:
+    def set_postfix(self, **kw):
+        pass
+
+
+@pytest.mark.parametrize("name,over", [
+    ("train_small_c2f", dict(barf_c2f=[0.0, 0.4], use_edges=False)),
+    ("train_small_edges", dict(barf_c2f=None, use_edges=True)),
+])
+def test_train_iteration_matches_reference_trajectory(tmp_path, name, over):
+    from marf_b200.attrdict import AttrDict
+    from marf_b200 import planar
+    g = cases.load_golden(name)
+    opt = _opt(tmp_path, H=40, W=56, patch_H=20, patch_W=28, batch_size=3, max_iter=40, use_masks=True,
+               arch=dict(layers=[None, 64, 64, 64, 3], skip=[], posenc=AttrDict(L_2D=4)), **over)
+    torch.manual_seed(3)
+    m = planar.Model(opt)
+    cfg = po.PlanarConfig(**dict(cases.SMALL, use_masks=True, max_iter=40, use_edges=bool(opt.use_edges),
+                                 barf_c2f=tuple(opt.barf_c2f) if opt.barf_c2f else None))
+    im = cases.make_images(cfg, seed=43)
+    m.images = AttrDict({k: (v.cuda() if v is not None else None) for k, v in im.items()})
+    m.build_networks()
+    # seed-matched initialisation (SURVEY.md §3.1 RNG order)
+    np.testing.assert_array_equal(m.graph.neural_image.mlp[0].weight.detach().cpu().numpy(), g["init_w0"])
+    np.testing.assert_array_equal(m.graph.neural_image.mlp[-1].weight.detach().cpu().numpy(), g["init_wl"])
+    m.graph.warp_param.weight.data.copy_(fx.synth_warp(33, 3, scale=0.03))
+    m.setup_optimizer()
+    m.setup_visualizer()
+    m.timer = AttrDict(start=0.0, it_mean=None)
+    var = AttrDict(idx=torch.arange(3), images=m.images)
+    hist = {k: [] for k in ("render", "rgb", "mask", "edge", "all")}
+    for _ in range(opt.max_iter):
+        loss = m.train_iteration(var, _Loader())
+        if opt.warp.fix_first:
+            m.graph.warp_param.weight.data[0] = 0
+        for k in hist:
+            hist[k].append(float(loss[k]))
+    for k in hist:
+        np.testing.assert_allclose(hist[k], g["hist_" + k], rtol=5e-3, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(m.graph.warp_param.weight.detach().cpu().numpy(), g["warp_final"], rtol=0, atol=3e-4)
+    assert float(m.graph.neural_image.progress) == pytest.approx(float(g["progress_final"]))
+    # forward-only render of the whole canvas
+    frame = m.predict_entire_image()
+    assert frame.shape == (3, 40, 56) and torch.isfinite(frame).all()
+    m.check_finite()
+
+
+def test_synthetic_scene_and_corner_metric(tmp_path):
+    from marf_b200.attrdict import AttrDict
+    from marf_b200 import planar
+    opt = _opt(tmp_path, H=64, W=96, patch_H=32, patch_W=48, batch_size=4, max_iter=30, use_masks=True, use_edges=False,
+               synthetic=dict(enabled=True, seed=1, occluders=True))
+    torch.manual_seed(0)
+    m = planar.Model(opt)
+    m.load_dataset()
+    assert m.images.rgb.shape == (4, 3, 32, 48) and m.images.masks.shape == (4, 1, 32, 48)
+    assert float(m.images.masks.min()) == 0.0 and float(m.images.rgb.max()) <= 1.0
+    m.build_networks()
+    m.setup_optimizer()
+    m.setup_visualizer()
+    m.timer = AttrDict(start=0.0, it_mean=None)
+    var = AttrDict(idx=torch.arange(4), images=m.images)
+    first = None
+    for _ in range(30):
+        loss = m.train_iteration(var, _Loader())
+        first = float(loss.rgb) if first is None else first
+    assert float(loss.rgb) < first          # the neural image is fitting the patches
+    err0 = float(m.corner_error_px(m.images.gt_warp))
+    assert np.isfinite(err0) and err0 > 0
+    # identical warps -> zero corner error
+    m.graph.warp_param.weight.data.copy_(m.images.gt_warp)
+    assert float(m.corner_error_px(m.images.gt_warp)) < 1e-4
