@@ -1,0 +1,302 @@
+"""bench.py — pixel-samples/s of MARF's planar bundle-adjusting training step (fwd + bwd + warp grad).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl marf|reference] [--precision fp32|bf16]
+                    [--workload config2|config4|config5]
+
+N=1 workload (BASELINE.json configs[1]): planar.yaml, full positional encoding (no barf_c2f), implicit mask
+network enabled, edge term on (yaml default), synthetic 360x480 scene, 5 patches of 180x240 -> 216,000
+pixel-samples per step.  N>1 (torchrun, one rank per GPU): weak scaling — every rank owns 5 such patches
+(B = 5N), gradients + loss sums all-reduced over NCCL every step.
+
+`value`  : whole-job pixel-samples/s of marf_step (+ all-reduce for N>1) with inputs resident in HBM, timed
+           with CUDA events per step on the launching stream, L2 flushed between steps, max over ranks.
+`e2e`    : the same metric through the reference-facing plugin (Model.train_iteration incl. Adam), with the
+           step's targets copied host->device from pinned memory and the loss read back, every step.
+`--impl reference` times the CPU oracle port (oracle/planar_oracle.py, eager PyTorch fp32 on all host cores —
+the reference itself is Python and cannot travel to the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PX = {  # algorithmic: 2 * MACs of fwd + dX + dW
+    "mlp256_L8": 1_236_480, "mlp256_L8_mask": 2_853_888, "mlp512_L10": 4_856_832,
+}
+
+
+def workload(name, n_gpus):
+    if name == "config2":
+        return dict(name="config2: planar.yaml full posenc + implicit mask network + edge term, synthetic 360x480, "
+                         f"{5 * n_gpus} patches 180x240 ({5} per GPU)",
+                    H=360, W=480, patch_H=180, patch_W=240, batch=5 * n_gpus, layers=[256, 256, 256, 256, 3], L=8,
+                    c2f=None, implicit=True, masks=True, edges=True, flop=FLOP_PER_PX["mlp256_L8_mask"], scaling="weak")
+    if name == "config4":
+        return dict(name="config4: 64 patches 1024x1024 of a synthetic 2048x2048 image, data-parallel",
+                    H=2048, W=2048, patch_H=1024, patch_W=1024, batch=64, layers=[256, 256, 256, 256, 3], L=8,
+                    c2f=None, implicit=False, masks=True, edges=False, flop=FLOP_PER_PX["mlp256_L8"], scaling="strong")
+    if name == "config5":
+        return dict(name="config5: width-512 MLP, L=10, 256 patches 512x512 of a synthetic 4096x4096 image "
+                         "(patch reduced from 2048x2048 for run time; FLOP/px unchanged)",
+                    H=4096, W=4096, patch_H=512, patch_W=512, batch=256, layers=[512, 512, 512, 512, 3], L=10,
+                    c2f=None, implicit=False, masks=True, edges=False, flop=FLOP_PER_PX["mlp512_L10"], scaling="strong")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_opt(wl, device, precision, out_dir):
+    from marf_b200 import options
+    opt = options.load_options("options/planar.yaml")
+    opt.update(model="planar", yaml="planar", H=wl["H"], W=wl["W"], patch_H=wl["patch_H"], patch_W=wl["patch_W"],
+               batch_size=wl["batch"], use_masks=wl["masks"], use_implicit_mask=wl["implicit"], use_edges=wl["edges"],
+               barf_c2f=wl["c2f"], use_homographies=False, precision=precision, device=device, output_path=out_dir,
+               tb=None, seed=3, world_size=int(os.environ.get("WORLD_SIZE", "1")), rank=int(os.environ.get("RANK", "0")))
+    opt.arch.layers = [None] + wl["layers"]
+    opt.arch.posenc.L_2D = wl["L"]
+    opt.synthetic = dict(enabled=True, seed=0, occluders=True)
+    opt.freq.scalar = 10 ** 9
+    opt.freq.vis = 10 ** 9
+    return opt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    hbm=d["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference(wl, steps, warmup, patches=1):
+    """Oracle port (eager PyTorch fp32 on the host cores) on a bounded sample: `patches` of the workload's patches."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fixtures as fx
+    import planar_oracle as po
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = po.PlanarConfig(H=wl["H"], W=wl["W"], patch_H=wl["patch_H"], patch_W=wl["patch_W"], batch_size=patches,
+                          layers=tuple([None] + wl["layers"]), L_2D=wl["L"], barf_c2f=wl["c2f"], use_masks=wl["masks"],
+                          use_implicit_mask=wl["implicit"], use_edges=wl["edges"])
+    if wl["implicit"] and (cfg.patch_H, cfg.patch_W) != (180, 240):
+        raise SystemExit("the reference's mask path is hard-wired to 180x240 patches")
+    params = po.init_params(cfg, seed=3)
+    rgb, masks = fx.synth_patches(0, patches, cfg.h, cfg.w, occluders=True)
+    images = dict(rgb=rgb, masks=masks if wl["masks"] else None, masks_eroded=None, edges=None)
+    if wl["masks"]:
+        images["masks_eroded"] = torch.from_numpy(po.erode5(masks.numpy()))
+    if wl["edges"]:
+        gray = (0.299 * rgb[:, 0:1] + 0.587 * rgb[:, 1:2] + 0.114 * rgb[:, 2:3])
+        images["edges"] = torch.from_numpy(po.sobel_gauss_edges(gray.numpy()))
+    n_px = patches * cfg.h * cfg.w
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        po.step(params, images, cfg, it=i)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return dict(value=n_px / sec, unit="pixel-samples/s", cores=cores, kind="port", torch_threads=torch.get_num_threads(),
+                sample=f"{patches} patch(es) of {cfg.h}x{cfg.w} = {n_px} pixel-samples per step, {len(times)} timed steps, "
+                       f"oracle/planar_oracle.py (eager PyTorch {torch.__version__} fp32 + autograd, the reference's own op sequence)",
+                ms_per_step=sec * 1e3), n_px
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload(args.workload, args.gpus)
+    steps = max(1, min(args.steps, 20))
+    base, n_px = cpu_reference(wl, steps=steps, warmup=min(args.warmup, 2), patches=1)
+    line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=base["value"], unit="pixel-samples/s", impl="reference",
+                n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2), ms_per_step=base["ms_per_step"], higher_is_better=True,
+                scaling=wl["scaling"], vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=wl["name"], sample=base["sample"]),
+                cpu_baseline=dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port", sample=base["sample"]),
+                e2e=dict(value=base["value"], unit="pixel-samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_marf(args):
+    import torch
+    import torch.distributed as dist
+    from marf_b200 import _lib as L
+    from marf_b200 import planar
+    from marf_b200.attrdict import AttrDict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    wl = workload(args.workload, args.gpus)
+    out_dir = os.path.join("/tmp", f"marf_bench_{os.getpid()}")
+    opt = make_opt(wl, device, args.precision, out_dir)
+    os.makedirs(out_dir, exist_ok=True)
+    torch.manual_seed(3)
+    m = planar.Model(opt)
+    m.load_dataset()
+    m.build_networks()
+    m.setup_optimizer()
+    m.vis_path = out_dir
+    m.timer = AttrDict(start=time.time(), it_mean=None)
+    g = m.graph
+    var = AttrDict(idx=torch.arange(opt.batch_size), images=m.images)
+    n_px_total = opt.batch_size * wl["patch_H"] * wl["patch_W"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
+    st = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident-input arm: marf_step (+ allreduce) only
+    for _ in range(max(3, args.warmup)):
+        g.forward(var, mode="train")
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = g.engine.launches
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        g.forward(var, mode="train")
+        e1.record(st)
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = g.engine.launches - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t)
+    ms_per_step = dev_ms / args.steps
+    value = n_px_total / (ms_per_step * 1e-3)
+
+    # ---------------- e2e arm: plugin call with host buffers (H2D of targets, D2H of the loss) + Adam
+    e = g.engine
+    host = {k: v.cpu().pin_memory() for k, v in dict(rgb=m.images.rgb).items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = 8
+
+    def e2e_step():
+        m.images.rgb.copy_(host["rgb"], non_blocking=True)
+        loss = m.train_iteration(var, None)
+        if opt.warp.fix_first:
+            g.warp_param.weight.data[0] = 0
+        return float(loss.all)                           # D2H read of the step's result
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(args.steps):
+        e2e_step()
+    e1.record(st)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / args.steps
+    e2e_value = n_px_total / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        tflops = value * wl["flop"] / 1e12
+        peak = pk["bf16_sustained"] * args.gpus
+        line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=value, unit="pixel-samples/s", n_gpus=args.gpus,
+                    steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True,
+                    scaling=wl["scaling"], vs_baseline=None, dtype="f32" if args.precision == "fp32" else "bf16 (fp32 accumulate)",
+                    data="synthetic",
+                    config=dict(workload=wl["name"], precision=args.precision, pixel_samples_per_step=n_px_total,
+                                flop_per_pixel_sample=wl["flop"], l2="flushed between timed steps (256 MiB memset)",
+                                timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                                wall_s_timed_loop=wall),
+                    clocks=clocks,
+                    e2e=dict(value=e2e_value, unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                             ms_per_step=e2e_ms, what="Model.train_iteration (fused step + Adam + fix_first) with pinned-host targets"),
+                    gpu_launches=launches,
+                    roofline=dict(bound="tensor", achieved=tflops, peak=peak, unit="TFLOP/s", frac=tflops / peak, traffic=None,
+                                  peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
+                                  note="achieved = algorithmic FLOP per step / mean step time; all kernels of the step"))
+        if args.gpus == 1 and not args.no_cpu:
+            base, _ = cpu_reference(wl, steps=3, warmup=1, patches=1)
+            line["cpu_baseline"] = dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port",
+                                        sample=base["sample"])
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="marf", choices=["marf", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MARF_BENCH_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    os.chdir(ROOT)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_marf(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,154 @@
+"""CPU-only checks: the C-ABI library builds/loads and exports every symbol include/marf_b200.h declares;
+host logic (options, sharding, coefficients); no compute calls (there is no GPU here and no CPU path)."""
+import ctypes as C
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from marf_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_header_symbols_exported(lib):
+    from marf_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "marf_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|int64_t|const char\*)\s+(marf_\w+)\s*\(", hdr, flags=re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.marf_abi_version() == _lib.MARF_ABI_VERSION
+
+
+def test_struct_layouts_match_header(lib):
+    """field order/count of the ctypes mirrors vs the C structs (names parsed from the header)."""
+    from marf_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "marf_b200.h")).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            decl = re.sub(r"^(const\s+)?(float|double|int32_t|uint32_t|int64_t)\s*(\*\s*const\s*\*|\*)?\s*", "", stmt)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part).strip())
+        return names
+    assert fields("marf_config") == [f[0] for f in _lib.MarfConfig._fields_]
+    assert fields("marf_step_io") == [f[0] for f in _lib.MarfStepIO._fields_]
+    assert fields("marf_render_io") == [f[0] for f in _lib.MarfRenderIO._fields_]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback(lib):
+    from marf_b200 import _lib
+    cfg = _lib.MarfConfig()
+    cfg.abi_version = _lib.MARF_ABI_VERSION
+    h = C.c_void_p()
+    rc = lib.marf_create(C.byref(cfg), C.byref(h))
+    assert rc == -3 and b"no CPU path" in lib.marf_last_error(None)
+    from marf_b200.engine import PlanarEngine
+    with pytest.raises(RuntimeError):
+        PlanarEngine(H=8, W=8, patch_H=4, patch_W=4, batch_size=1, layers=[3])
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from marf_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.load()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "marf_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "planar_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_argument_parser_semantics():
+    from marf_b200 import options
+    o = options.parse_arguments(["--model=planar", "--yaml=planar", "--barf_c2f=[0,0.4]", "--arch.posenc!", "--seed=3",
+                                 "--load=", "--use_implicit_mask"])
+    assert o.model == "planar" and o.barf_c2f == [0, 0.4] and o.arch.posenc is False and o.seed == 3
+    assert o.load is None and o.use_implicit_mask is True
+    with pytest.raises(ValueError):
+        options.parse_arguments(["--a=1", "--a=2"])
+    with pytest.raises(ValueError):
+        options.parse_arguments(["a=1"])
+
+
+def test_yaml_defaults_match_reference_planar_yaml():
+    from marf_b200 import options
+    opt = options.load_options("options/planar.yaml")
+    assert (opt.H, opt.W, opt.patch_H, opt.patch_W, opt.batch_size, opt.max_iter) == (360, 480, 180, 240, 5, 3000)
+    assert opt.arch.layers == [None, 256, 256, 256, 256, 3] and opt.arch.skip == [] and opt.arch.posenc.L_2D == 8
+    assert opt.barf_c2f is None and opt.use_masks is True and opt.use_implicit_mask is False and opt.use_edges is True
+    assert opt.loss_weight == dict(render=0, rgb=0, edge=0, mask=0)
+    assert (opt.optim.lr, opt.optim.lr_warp, opt.optim.lr_mask, opt.optim.algo) == (1e-3, 1e-3, 1e-3, "Adam")
+    assert opt.warp.fix_first is True and opt.warp.dof == 8 and opt.N_vocab == 1500
+    # unknown keys are refused when stdin is not a TTY (the reference prompts)
+    with pytest.raises(KeyError):
+        options.override_options(opt, options.parse_arguments(["--not_a_key=1"]), key_stack=[], safe_check=True)
+
+
+def test_override_and_inheritance(tmp_path, monkeypatch):
+    from marf_b200 import options
+    (tmp_path / "options").mkdir()
+    (tmp_path / "options" / "base.yaml").write_text("a: 1\nb:\n    c: 2\n    d: 3\n")
+    (tmp_path / "options" / "child.yaml").write_text("_parent_: options/base.yaml\nb:\n    c: 5\ne: 6\n")
+    monkeypatch.chdir(tmp_path)
+    opt = options.load_options("options/child.yaml")
+    assert opt.a == 1 and opt.b.c == 5 and opt.b.d == 3 and opt.e == 6
+
+
+def test_shard_plan():
+    from marf_b200.engine import shard_plan
+    assert shard_plan(5, 180, 0, 1) == (5, 0, 180, 0)
+    assert [shard_plan(64, 1024, r, 8) for r in (0, 7)] == [(8, 0, 1024, 0), (8, 56, 1024, 0)]
+    parts = [shard_plan(5, 180, r, 8) for r in range(8)]            # rows split when patches do not divide
+    assert all(p[0] == 5 and p[1] == 0 for p in parts)
+    assert sum(p[2] for p in parts) == 180 and parts[0][3] == 0
+    for a, b in zip(parts[:-1], parts[1:]):
+        assert a[3] + a[2] == b[3]
+
+
+def test_loss_coefficients_match_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import planar_oracle as po
+    from marf_b200.attrdict import AttrDict
+    from marf_b200.planar import Graph
+    for lw in (dict(render=0, rgb=0, edge=0, mask=0), dict(render=0, rgb=-1, edge=0.5, mask=None), dict(render=1, rgb=None, edge=0, mask=0)):
+        for use_edges in (False, True):
+            cfg = po.PlanarConfig(use_edges=use_edges, loss_weight=dict(lw), max_iter=200)
+            fake = AttrDict(opt=AttrDict(use_edges=use_edges, alpha_initial=0.0, alpha_final=1.0, loss_weight=AttrDict(lw)),
+                            it=60, max_iter=200)
+            got = Graph.loss_coefficients(fake)
+            assert got[:3] == pytest.approx(po.loss_coefficients(cfg, 60))
+            assert got[3] == pytest.approx(po.edge_alpha(cfg, 60))
+
+
+def test_attrdict():
+    from marf_b200.attrdict import AttrDict
+    d = AttrDict(a=1, b=dict(c=[dict(x=1)], d=None))
+    assert d.b.c[0].x == 1 and d["b"]["d"] is None
+    d.e = dict(f=2)
+    assert d.e.f == 2 and d.to_dict() == {"a": 1, "b": {"c": [{"x": 1}], "d": None}, "e": {"f": 2}}
+    assert d.pop("a") == 1 and "a" not in d
+    with pytest.raises(AttributeError):
+        d.missing
