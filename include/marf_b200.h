@@ -171,6 +171,12 @@ int marf_warp_points(marf_handle* h, const float* xy, const float* warp, int32_t
 int marf_compute_edges(marf_handle* h, const float* images, int32_t n, int32_t c, int32_t rows, int32_t w,
                        double* out, void* stream);
 
+/* diagnostic: run ONE tensor-core kernel (tcgen05) on fp32 device arrays that are rounded to bf16 inside.
+ * mode 0: relu(A[rows,K] W[N,K]^T + aux[N]); 1: (A W^T)*(aux[rows,N]>0); 2: plain fp32 out, N=64;
+ * 3: out[N,K] = A[rows,N]^T aux[rows,K] (the dW kernel).  Synchronises `stream`.  Used by tests/ only. */
+int marf_tc_selftest(int device, int mode, int rows, int K, int N, const float* A, const float* W, const float* aux,
+                     float* out, void* stream);
+
 /* bookkeeping for bench.py / tests: kernels launched by this handle since creation, bytes of workspace. */
 int64_t marf_launch_count(const marf_handle* h);
 int64_t marf_workspace_bytes(const marf_handle* h);

@@ -63,7 +63,7 @@ void set_schedule(marf_handle* h, float progress) {
 
 // ------------------------------------------------------------------------------------------------
 static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_in0, uint32_t skip_mask, int d_in,
-                       bool need_dx0) {
+                       bool need_dx0, int act_rows) {
   C.n = n;
   C.skip_mask = skip_mask;
   C.d_in = d_in;
@@ -93,7 +93,7 @@ static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_i
   }
   for (int l = 0; l <= n; ++l) {
     int ld = l < n ? C.ld_in[l] : C.ld_out[n - 1];
-    C.act[l] = (float*)ws_alloc(h, (size_t)h->chunk * ld * sizeof(float));
+    C.act[l] = act_rows > 0 ? (float*)ws_alloc(h, (size_t)act_rows * ld * sizeof(float)) : (float*)ws_alloc(h, 16);
     if (!C.act[l]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (activations)");
   }
   return MARF_OK;
@@ -174,20 +174,24 @@ extern "C" int marf_create(const marf_config* cfg, marf_handle** out) {
   g.d_in = c.L > 0 ? 2 + 4 * c.L : 2;
   set_schedule(h, 0.f);
   h->n_local = (long long)c.batch * c.rows * ww;
-  long long max_chunk = c.max_chunk_pixels > 0 ? c.max_chunk_pixels : (c.precision == MARF_BF16 ? (1ll << 17) : (1ll << 19));
+  long long max_chunk = c.max_chunk_pixels > 0 ? c.max_chunk_pixels : (c.precision == MARF_BF16 ? (1ll << 20) : (1ll << 19));
   // the render path traverses up to H*W pixels per patch with the same buffers
   h->chunk = (int)round_up(std::min<long long>(std::max<long long>(h->n_local, 128), max_chunk), 128);
   h->n_chunks = (int)((h->n_local + h->chunk - 1) / h->chunk);
+  // fp32 activation buffers: the whole chunk in fp32 mode; in bf16 mode only the forward-only render uses them
+  const bool f32 = c.precision == MARF_FP32;
+  h->render_rows = f32 ? h->chunk : std::min(h->chunk, 1 << 16);
 
-  int rc = build_chain(h, h->img, c.n_layers, c.layer_out, g.d_in, c.skip_mask, g.d_in, true);
+  int rc = build_chain(h, h->img, c.n_layers, c.layer_out, g.d_in, c.skip_mask, g.d_in, true, h->render_rows);
   if (rc == MARF_OK && c.mask_mode == MARF_MASK_IMPLICIT)
-    rc = build_chain(h, h->msk, c.mask_n_layers, c.mask_layer_out, 3 * c.mask_embed_dim + 2 + 4 * c.mask_uv_freqs, 0, 0, false);
+    rc = build_chain(h, h->msk, c.mask_n_layers, c.mask_layer_out, 3 * c.mask_embed_dim + 2 + 4 * c.mask_uv_freqs, 0, 0, false,
+                     f32 ? h->chunk : 0);
   if (rc != MARF_OK) { std::string e = h->err; marf_destroy(h); g_create_err = e; return rc; }
   int max_ld = std::max(h->img.max_ld, c.mask_mode == MARF_MASK_IMPLICIT ? h->msk.max_ld : 0);
   h->Hm = (float*)ws_alloc(h, (size_t)c.batch_global * 9 * sizeof(float));
   h->G = (double*)ws_alloc(h, (size_t)c.batch * 9 * sizeof(double));
-  h->dYa = (float*)ws_alloc(h, (size_t)h->chunk * max_ld * sizeof(float));
-  h->dYb = (float*)ws_alloc(h, (size_t)h->chunk * max_ld * sizeof(float));
+  h->dYa = (float*)ws_alloc(h, f32 ? (size_t)h->chunk * max_ld * sizeof(float) : 16);
+  h->dYb = (float*)ws_alloc(h, f32 ? (size_t)h->chunk * max_ld * sizeof(float) : 16);
   h->coef = (LossCoef*)ws_alloc(h, sizeof(LossCoef));
   h->sums_static = (double*)ws_alloc(h, 4 * sizeof(double));
   bool ok = h->Hm && h->G && h->dYa && h->dYb && h->coef && h->sums_static;
@@ -497,7 +501,12 @@ static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t 
   return rc;
 }
 
-static double static_norm_none(const marf_handle* h) { return 3.0 * (double)h->n_local; }
+namespace marf {
+int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return begin_step(h, io, st); }
+int engine_edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return edge_pass(h, io, st); }
+int engine_begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return begin_backward(h, io, st, nullptr); }
+int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return finish_backward(h, io, st); }
+}  // namespace marf
 
 static int fp32_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   int rc = begin_step(h, io, st);
@@ -535,16 +544,14 @@ static int fp32_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st
 extern "C" int marf_step_forward(marf_handle* h, const marf_step_io* io, void* stream) {
   int rc = validate_io(h, io);
   if (rc) return rc;
-  if (h->cfg.precision != MARF_FP32)
-    return fail(h, MARF_ERR_UNSUPPORTED, "two-phase stepping is implemented for precision=fp32; bf16 uses marf_step");
+  if (h->cfg.precision == MARF_BF16) return bf16_forward(h, io, (cudaStream_t)stream);
   return fp32_forward(h, io, (cudaStream_t)stream);
 }
 
 extern "C" int marf_step_backward(marf_handle* h, const marf_step_io* io, void* stream) {
   int rc = validate_io(h, io);
   if (rc) return rc;
-  if (h->cfg.precision != MARF_FP32)
-    return fail(h, MARF_ERR_UNSUPPORTED, "two-phase stepping is implemented for precision=fp32; bf16 uses marf_step");
+  if (h->cfg.precision == MARF_BF16) return bf16_backward(h, io, (cudaStream_t)stream);
   return fp32_backward(h, io, (cudaStream_t)stream);
 }
 
@@ -584,10 +591,10 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
     LAUNCH_CHECK(h);
   }
   long long n = (long long)io->n_patches * g.h * g.w;
-  for (long long first = 0; first < n; first += h->chunk) {
+  for (long long first = 0; first < n; first += h->render_rows) {
     PxRange rg;
     rg.first = first;
-    rg.count = (int)std::min<long long>(h->chunk, n - first);
+    rg.count = (int)std::min<long long>(h->render_rows, n - first);
     rg.padded = (int)round_up(rg.count, 128);
     k_encode<<<(rg.padded + 127) / 128, 128, 0, st>>>(g, rg, h->Hm, io->warp ? 0 : 1, h->img.act[0], h->img.ld_in[0]);
     LAUNCH_CHECK(h);

@@ -30,6 +30,7 @@ struct marf_handle {
   long long n_local;           // batch*rows*w
   int chunk;                   // padded pixel-samples per pass (multiple of 128)
   int n_chunks;
+  int render_rows;             // rows of the fp32 activation buffers (forward-only render path)
   marf::Chain img, msk;
   float* Hm = nullptr;         // [batch_global,9]
   double* G = nullptr;         // [batch,9]
@@ -62,5 +63,7 @@ void set_schedule(marf_handle* h, float progress);
 int bf16_create(marf_handle* h);
 void bf16_destroy(marf_handle* h);
 int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st);
+int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st);
+int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st);
 bool bf16_supported(const marf_handle* h, const marf_step_io* io, std::string* why);
 }  // namespace marf

@@ -53,7 +53,7 @@ __device__ __forceinline__ void sl3_generator(const float* h, double* A) {
   A[6] = h[6]; A[7] = h[7]; A[8] = h[5];
 }
 
-__global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
+static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n) return;
   double A[9], E[9];
@@ -64,7 +64,7 @@ __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __res
 }
 
 // G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches)
-__global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
+static __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
                                int n_local, float* __restrict__ g_warp) {
   int bl = blockIdx.x * blockDim.x + threadIdx.x;
   if (bl >= n_local) return;
@@ -94,7 +94,7 @@ __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __r
 }
 
 // warped crop corners (warp.py:83-93): [(X0,Y0),(X0,Y1),(X1,Y1),(X1,Y0)]
-__global__ void k_warp_corners(Geo g, const float* __restrict__ Hm, int n, float* __restrict__ out) {
+static __global__ void k_warp_corners(Geo g, const float* __restrict__ Hm, int n, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 4) return;
   int b = i / 4, c = i % 4;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int
   c = rem - (rem / g.w) * g.w;
 }
 
-__global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [batch_global,9] or identity */,
+static __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [batch_global,9] or identity */,
                          int identity, float* __restrict__ X0, int ld) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
@@ -164,7 +164,7 @@ __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [bat
 }
 
 // backward of the prologue: dX0 [n,ld] -> per-patch G = sum_p dq (x) [x,y,1]  (SURVEY.md §8 a-4,a-5)
-__global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ Hm, const float* __restrict__ dX0,
+static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ Hm, const float* __restrict__ dX0,
                                   int ld, double* __restrict__ G /* [batch,9] local patches */) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < rg.count;
@@ -214,7 +214,7 @@ __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ H
 // mask-head input features (model/planar.py:342-349, :491-518): [E[trunc r], E[trunc g], E[trunc b], PosEmbedding(xy)]
 // one block of 128 threads per pixel-sample row; iteration-invariant (cached by the engine when possible).
 // ============================================================================================
-__global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
+static __global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
                                 int embed_dim, int n_freqs, float* __restrict__ F, int ld) {
   int t = blockIdx.x;
   float* o = F + (size_t)t * ld;
@@ -292,7 +292,7 @@ __device__ __forceinline__ void load_tile(float (*S)[GBM], const float* __restri
 }
 
 template <bool A_KC, bool B_KC, int TN, int EPI>
-__global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
+static __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float* __restrict__ A, int lda,
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                const float* __restrict__ aux, int ldaux, int k_split) {
   constexpr int BN = 16 * TN;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const float*
 }
 
 // db[j] += sum_m dY[m,j]
-__global__ void k_colsum(int M, int N, const float* __restrict__ dY, int ld, float* __restrict__ db, int rows_per_block) {
+static __global__ void k_colsum(int M, int N, const float* __restrict__ dY, int ld, float* __restrict__ db, int rows_per_block) {
   __shared__ float red[8][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int n = blockIdx.x * 32 + tx;
@@ -386,20 +386,20 @@ __global__ void k_colsum(int M, int N, const float* __restrict__ dY, int ld, flo
 }
 
 // weight (un)packing between torch layouts and the padded workspace
-__global__ void k_pack(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp, int prow, int pcol) {
+static __global__ void k_pack(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp, int prow, int pcol) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= prow * pcol) return;
   int r = i / pcol, c = i - r * pcol;
   Wp[i] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f;
 }
-__global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* __restrict__ W, int rows, int cols) {
+static __global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* __restrict__ W, int rows, int cols) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   int r = i / cols, c = i - r * cols;
   W[i] = Wp[(size_t)r * pcol + c];
 }
 // copy `cols` columns between row-major buffers (skip-connection concat / split)
-__global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int lds, int soff, float* __restrict__ dst,
+static __global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int lds, int soff, float* __restrict__ dst,
                             int ldd, int doff, int accumulate) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * cols) return;
@@ -409,7 +409,7 @@ __global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int 
   *d = accumulate ? *d + v : v;
 }
 // dY_prev[m,j] = dX[m,j] * (act[m,j] > 0) for j < cols
-__global__ void k_relu_mask(int M, int cols, const float* __restrict__ dX, int ldx, const float* __restrict__ act,
+static __global__ void k_relu_mask(int M, int cols, const float* __restrict__ dX, int ldx, const float* __restrict__ act,
                             int lda, float* __restrict__ dY, int ldy) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * cols) return;
@@ -430,7 +430,7 @@ struct LossArgs {
   float* mask_pred;            // optional [n_total]
 };
 
-__global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__ sums) {
+static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__ sums) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   double s_rgb = 0, n_rgb = 0, s_mask = 0, n_mask = 0, bad = 0;
   if (t < rg.count) {
@@ -472,7 +472,7 @@ __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__
 }
 
 // static mask sum (disk masks): N_RGB = 3 * sum m over the local shard
-__global__ void k_sum_f32(const float* __restrict__ x, long long n, double scale, double* __restrict__ out) {
+static __global__ void k_sum_f32(const float* __restrict__ x, long long n, double scale, double* __restrict__ out) {
   double s = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s += (double)x[i];
@@ -489,7 +489,7 @@ struct EdgeArgs {
   const float* masks_eroded;   // disk mode
   const float* mask_pred;      // implicit mode [n_total]
 };
-__global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __restrict__ sums) {
+static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __restrict__ sums) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double s = 0, nn = 0;
   if (i < n_total) {
@@ -511,7 +511,7 @@ __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __res
 }
 
 // resolve normalisers on device (after an optional all-reduce of `sums`): no host round trip
-__global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
+static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
                             int use_edges, LossCoef* __restrict__ out) {
   double n_rgb = norm_rgb_host > 0 ? norm_rgb_host : sums[MARF_N_RGB];
   double n_edge = norm_edge_host > 0 ? norm_edge_host : sums[MARF_N_EDGE];
@@ -534,7 +534,7 @@ struct GradArgs {
   float* dmlogits; int dmld;   // out [n_pad, dmld] (implicit only)
 };
 
-__global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
+static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
   float* dl = a.dlogits + (size_t)t * a.dld;
@@ -581,7 +581,7 @@ __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __res
 }
 
 // plain sigmoid of the first 3 columns (render path)
-__global__ void k_sigmoid_out(int n, const float* __restrict__ logits, int ld, float* __restrict__ out) {
+static __global__ void k_sigmoid_out(int n, const float* __restrict__ logits, int ld, float* __restrict__ out) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
 #pragma unroll
@@ -598,7 +598,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-__global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int rows, int w, int interleaved,
+static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int rows, int w, int interleaved,
                             double* __restrict__ mag /* planar [n,ch,rows,w] */) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)n * ch * rows * w;
@@ -625,7 +625,7 @@ __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int ro
   mag[i] = sqrt(gx * gx + gy * gy);
 }
 
-__global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
+static __global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)planes * rows * w;
   if (i >= total) return;

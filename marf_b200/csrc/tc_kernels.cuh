@@ -1,0 +1,340 @@
+// tcgen05 kernels of the bf16 tensor-core path (sm_100a).
+//
+//   k_tc_gemm<N_TILE,EPI> : C[128-row tiles, N_TILE] = epi(A[rows,K] * W[N,K]^T), A streamed by TMA, W resident in SMEM,
+//                           fp32 accumulators double-buffered in TMEM, epilogue through SMEM + TMA store.
+//                           Used for the forward layers (bias+ReLU) and the dX layers (ReLU mask of the layer input).
+//   k_tc_dw<N_TILE>       : dW[out,in] += dY[rows,out]^T * X[rows,in] (contraction over pixel rows, both operands
+//                           MN-major straight from the row-major activations), split over CTAs, fp32 red.add at the end.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue
+// (warp w owns TMEM lanes 32*(w%4)..+31 = tile rows).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tc_ptx.cuh"
+
+namespace marf {
+namespace tc {
+
+constexpr int kTileM = 128;          // pixel rows per tile (= TMEM lanes)
+constexpr int kChunkK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int kChunkBytes = kTileM * 128;   // one [128 x 64] bf16 operand chunk
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+
+enum { EPI_BIAS_RELU = 0, EPI_RELU_MASK = 1, EPI_PLAIN_F32 = 2 };
+
+struct GemmParams {
+  int n_tiles;          // 128-row tiles
+  int k_chunks;         // K / 64
+  const float* bias;    // [N] (EPI_BIAS_RELU)
+  float* out_f32;       // EPI_PLAIN_F32: [rows, ld_out] fp32, first n_store columns written
+  int ld_out;
+  int n_store;
+};
+
+struct GemmSmem {       // offsets computed on host and device identically
+  int w_bytes, a_off, out_off, bias_off, bar_off, total;
+};
+__host__ __device__ inline GemmSmem gemm_smem(int n_tile, int k_chunks, bool staged_out) {
+  GemmSmem s;
+  s.w_bytes = k_chunks * n_tile * 128;
+  s.a_off = s.w_bytes;
+  s.out_off = s.a_off + kStages * kChunkBytes;
+  s.bias_off = s.out_off + (staged_out ? 2 * kChunkBytes : 0);
+  s.bar_off = s.bias_off + n_tile * 4;
+  s.total = s.bar_off + 256;
+  return s;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int N_TILE, int EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask, GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kStaged = EPI != EPI_PLAIN_F32;
+  constexpr int kSlabs = N_TILE / 64;
+  constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
+  const GemmSmem L = gemm_smem(N_TILE, p.k_chunks, kStaged);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + L.a_off;
+  uint8_t* sOut = smem + L.out_off;
+  float* sBias = reinterpret_cast<float*>(smem + L.bias_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;                 // [kStages]
+  uint64_t* empty = bars + kStages;      // [kStages]
+  uint64_t* w_full = bars + 2 * kStages;
+  uint64_t* acc_full = w_full + 1;       // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint64_t* mask_full = acc_empty + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * N_TILE;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmW);
+    if (kStaged) prefetch_tmap(&tmOut);
+    if (EPI == EPI_RELU_MASK) prefetch_tmap(&tmMask);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(w_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); mbar_init(&mask_full[a], 1); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  if (EPI == EPI_BIAS_RELU && warp >= 2)
+    for (int i = threadIdx.x - 64; i < N_TILE; i += 128) sBias[i] = p.bias[n0 + i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
+      for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &tmW, c * kChunkK, n0, w_full);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int c = 0; c < p.k_chunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], kChunkBytes);
+          tma_load_2d(sA + s * kChunkBytes, &tmA, c * kChunkK, tile * kTileM, &full[s]);
+        }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kTileM, N_TILE, 0, 0);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      uint32_t it = 0, t_iter = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_iter) {
+        const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
+        mbar_wait(&acc_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * N_TILE;
+        for (int c = 0; c < p.k_chunks; ++c, ++it) {
+          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t da = smem_desc_sw128(smem_u32(sA + s * kChunkBytes), 16, 1024);
+          const uint64_t db = smem_desc_sw128(smem_u32(sW + c * N_TILE * 128), 16, 1024);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(d_tmem, da + 2 * j, db + 2 * j, idesc, (c | j) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[a]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (128 threads)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                       // tile row == TMEM lane
+    const bool leader = threadIdx.x == 64;
+    const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+    uint32_t g = 0, t_iter = 0;
+    if (EPI == EPI_RELU_MASK && leader && (int)blockIdx.x < p.n_tiles) {
+      mbar_expect_tx(&mask_full[0], kChunkBytes);
+      tma_load_2d(sOut, &tmMask, n0, blockIdx.x * kTileM, &mask_full[0]);
+    }
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_iter) {
+      const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
+      mbar_wait(&acc_full[a], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < kSlabs; ++j, ++g) {
+        const uint32_t b = g & 1;
+        uint8_t* ob = sOut + b * kChunkBytes;
+        if (EPI == EPI_RELU_MASK) {
+          if (leader) {
+            // the other buffer is free once the store issued for the previous slab has finished reading it
+            bulk_wait_read<0>();
+            int nt = tile, nj = j + 1;
+            if (nj == kSlabs) { nj = 0; nt = tile + gridDim.x; }
+            if (nt < p.n_tiles) {
+              mbar_expect_tx(&mask_full[b ^ 1], kChunkBytes);
+              tma_load_2d(sOut + (b ^ 1) * kChunkBytes, &tmMask, n0 + nj * 64, nt * kTileM, &mask_full[b ^ 1]);
+            }
+          }
+          mbar_wait(&mask_full[b], (g >> 1) & 1);
+        } else if (EPI == EPI_BIAS_RELU) {
+          if (leader) bulk_wait_read<1>();             // the store issued two slabs ago (same buffer) is done reading
+          named_bar_sync(1, 128);
+        }
+        uint32_t v[64];
+        {
+          uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * N_TILE + j * 64;
+          tmem_ld32(taddr, v0);
+          tmem_ld32(taddr + 32, v1);
+          tmem_ld_wait();
+        }
+        if (EPI == EPI_PLAIN_F32) {
+          float* o = p.out_f32 + (size_t)(tile * kTileM + r) * p.ld_out + n0 + j * 64;
+#pragma unroll
+          for (int c4 = 0; c4 < 16; ++c4)
+            if (n0 + j * 64 + c4 * 4 < p.n_store)
+              *reinterpret_cast<uint4*>(o + c4 * 4) = make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint8_t* addr = ob + sw_row + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4);
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i * 8 + e]);
+            if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e] + sBias[j * 64 + i * 8 + e], 0.f);
+            } else {
+              const uint4 m = *reinterpret_cast<const uint4*>(addr);
+              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+                const uint32_t h = (mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+                f[e] = ((h & 0x8000u) == 0 && (h & 0x7FFFu) != 0) ? f[e] : 0.f;
+              }
+            }
+            *reinterpret_cast<uint4*>(addr) =
+                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(2, 128);
+          if (leader) {
+            tma_store_2d(&tmOut, n0 + j * 64, tile * kTileM, ob);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+    if (kStaged && leader) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ================================================================================================
+// dW[out, in] += sum over pixel rows of dY[row, out] * X[row, in]
+// ================================================================================================
+struct DwParams {
+  int rows;             // padded pixel rows (multiple of 64)
+  int rows_per_cta;     // multiple of 64
+  int m_halves;         // ceil(out / 128)
+  int m_valid;          // out features
+  int n_valid;          // in features
+  float* dW;            // [out, ld_w] fp32, accumulated with red.add
+  int ld_w;
+};
+constexpr int kDwStages = 3;
+constexpr int kDwRows = 64;                 // pixel rows per stage
+constexpr int kDwSlab = kDwRows * 128;      // [64 rows x 64 cols] bf16
+
+template <int N_TILE>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int kBSlabs = N_TILE / 64;
+  const int a_slabs = p.m_halves * 2;
+  const int stage_bytes = (a_slabs + kBSlabs) * kDwSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDwStages;
+  uint64_t* done = bars + 2 * kDwStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const uint32_t tmem_cols = 512;   // m_halves * N_TILE <= 512
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * N_TILE;
+  const int row_begin = blockIdx.x * p.rows_per_cta;
+  const int row_end = min(p.rows, row_begin + p.rows_per_cta);
+  const int n_iter = row_begin < row_end ? (row_end - row_begin) / kDwRows : 0;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmDY);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, tmem_cols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_iter > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < n_iter; ++it) {
+          const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+          uint8_t* st = smem + s * stage_bytes;
+          const int row = row_begin + it * kDwRows;
+          for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &tmDY, i * 64, row, &full[s]);
+          for (int i = 0; i < kBSlabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &tmX, n0 + i * 64, row, &full[s]);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = idesc_bf16(128, N_TILE, 1, 1);     // both operands MN-major
+        for (int it = 0; it < n_iter; ++it) {
+          const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < kDwRows / 16; ++ks) {
+            const uint64_t db = smem_desc_sw128(st + a_slabs * kDwSlab + ks * 2048, kDwSlab, 1024);
+            for (int mh = 0; mh < p.m_halves; ++mh) {
+              const uint64_t da = smem_desc_sw128(st + mh * 2 * kDwSlab + ks * 2048, kDwSlab, 1024);
+              umma_bf16(tmem_base + mh * N_TILE, da, db, idesc, (it | ks) != 0);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(done);
+      }
+    } else {
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      mbar_wait(done, 0);
+      tc_fence_after();
+      for (int mh = 0; mh < p.m_halves; ++mh) {
+        const int m = mh * 128 + r;
+#pragma unroll 1
+        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * N_TILE + c0, v);
+          tmem_ld_wait();
+          if (m < p.m_valid) {
+            float* o = p.dW + (size_t)m * p.ld_w + n0 + c0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (n0 + c0 + e < p.n_valid) atomicAdd(o + e, __uint_as_float(v[e]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
+}
+
+}  // namespace tc
+}  // namespace marf
