@@ -405,7 +405,7 @@ static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-    k_loss_stats<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, a, io->loss_sums);
+    k_loss_stats<<<std::min((rg.padded + 255) / 256, 592), 256, 0, st>>>(h->geo, rg, a, io->loss_sums);
     LAUNCH_CHECK(h);
   }
   return MARF_OK;
@@ -452,7 +452,7 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   float* dx0 = nullptr;
   int rc = chain_backward(h, st, h->img, rg.padded, &dx0);
   if (rc) return rc;
-  k_encode_backward<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, h->Hm, dx0, h->img.ld_in[0], h->G);
+  k_encode_backward<<<(rg.padded + 255) / 256, 256, 0, st>>>(h->geo, rg, h->Hm, dx0, h->img.ld_in[0], h->G);
   LAUNCH_CHECK(h);
   if (implicit) {
     ga.dlogits = h->dYb;                       // scratch (ignored)
@@ -465,18 +465,20 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   return MARF_OK;
 }
 
-static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32 = true) {
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = refresh_data(h, io, st);
   if (rc) return rc;
   set_schedule(h, io->progress);
-  rc = pack_chain(h, st, h->img, io->mlp_w, io->mlp_b);
-  if (rc) return rc;
-  if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
-    rc = pack_chain(h, st, h->msk, io->mask_w, io->mask_b);
+  if (pack_fp32) {
+    rc = pack_chain(h, st, h->img, io->mlp_w, io->mlp_b);
     if (rc) return rc;
+    if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
+      rc = pack_chain(h, st, h->msk, io->mask_w, io->mask_b);
+      if (rc) return rc;
+    }
   }
-  k_sl3_to_SL3<<<(h->cfg.batch_global + 63) / 64, 64, 0, st>>>(io->warp, h->cfg.batch_global, h->Hm);
+  k_sl3_to_SL3<<<h->cfg.batch_global, 64, 0, st>>>(io->warp, h->cfg.batch_global, h->Hm);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -490,11 +492,12 @@ static int begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t s
   return MARF_OK;
 }
 
-static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack = true) {
   if (!io->g_warp) return fail(h, MARF_ERR_INVALID, "missing g_warp");
   CUDA_TRY(h, cudaMemsetAsync(io->g_warp, 0, (size_t)h->cfg.batch_global * 8 * sizeof(float), st));
-  k_sl3_backward<<<(h->cfg.batch + 63) / 64, 64, 0, st>>>(io->warp, h->G, h->cfg.patch_offset, h->cfg.batch, io->g_warp);
+  k_sl3_backward<<<h->cfg.batch, 64, 0, st>>>(io->warp, h->G, h->cfg.patch_offset, h->cfg.batch, io->g_warp);
   LAUNCH_CHECK(h);
+  if (!unpack) return MARF_OK;
   int rc = unpack_chain(h, st, h->img, io->g_mlp_w, io->g_mlp_b);
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) rc = unpack_chain(h, st, h->msk, io->g_mask_w, io->g_mask_b);
@@ -502,10 +505,10 @@ static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t 
 }
 
 namespace marf {
-int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return begin_step(h, io, st); }
+int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32) { return begin_step(h, io, st, pack_fp32); }
 int engine_edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return edge_pass(h, io, st); }
 int engine_begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return begin_backward(h, io, st, nullptr); }
-int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return finish_backward(h, io, st); }
+int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack) { return finish_backward(h, io, st, unpack); }
 }  // namespace marf
 
 static int fp32_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
@@ -587,7 +590,7 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
   g.x0 = io->crop ? c.W / 2 - c.patch_W / 2 : 0;
   g.rows = g.h; g.row_offset = 0; g.patch_offset = 0;
   if (io->warp) {
-    k_sl3_to_SL3<<<(io->n_patches + 63) / 64, 64, 0, st>>>(io->warp, io->n_patches, h->Hm);
+    k_sl3_to_SL3<<<io->n_patches, 64, 0, st>>>(io->warp, io->n_patches, h->Hm);
     LAUNCH_CHECK(h);
   }
   long long n = (long long)io->n_patches * g.h * g.w;
@@ -612,7 +615,7 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
 extern "C" int marf_sl3_to_SL3(marf_handle* h, const float* warp, int32_t n, float* out9, void* stream) {
   if (!h) return MARF_ERR_INVALID;
   if (!warp || !out9 || n <= 0) return fail(h, MARF_ERR_INVALID, "bad sl3 args");
-  k_sl3_to_SL3<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(warp, n, out9);
+  k_sl3_to_SL3<<<n, 64, 0, (cudaStream_t)stream>>>(warp, n, out9);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -621,7 +624,7 @@ extern "C" int marf_warp_corners(marf_handle* h, const float* warp, int32_t n, f
   if (!h) return MARF_ERR_INVALID;
   if (!warp || !out || n <= 0 || n > h->cfg.batch_global) return fail(h, MARF_ERR_INVALID, "bad corner args");
   cudaStream_t st = (cudaStream_t)stream;
-  k_sl3_to_SL3<<<(n + 63) / 64, 64, 0, st>>>(warp, n, h->Hm);
+  k_sl3_to_SL3<<<n, 64, 0, st>>>(warp, n, h->Hm);
   LAUNCH_CHECK(h);
   Geo g = h->geo;
   g.h = h->cfg.patch_H; g.w = h->cfg.patch_W;
@@ -648,7 +651,7 @@ extern "C" int marf_warp_points(marf_handle* h, const float* xy, const float* wa
   cudaStream_t st = (cudaStream_t)stream;
   float* Hm = nullptr;
   CUDA_TRY(h, cudaMallocAsync((void**)&Hm, (size_t)n * 9 * sizeof(float), st));
-  k_sl3_to_SL3<<<(n + 63) / 64, 64, 0, st>>>(warp, n, Hm);
+  k_sl3_to_SL3<<<n, 64, 0, st>>>(warp, n, Hm);
   LAUNCH_CHECK(h);
   long long tot = (long long)n * p;
   k_warp_points<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(xy, Hm, n, p, out);

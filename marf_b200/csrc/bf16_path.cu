@@ -102,60 +102,74 @@ __global__ void k_pack_bf16(const float* __restrict__ W, int rows, int cols, bf1
 }
 
 // thin output layer (k_out <= 4): logits[row, o] = b[o] + sum_k X[row,k] W[o,k]      (fp32 out [n, 4])
-template <int OUT>
-__global__ void k_thin_fwd(int n, int width, const bf16* __restrict__ X, int ld, const float* __restrict__ W,
+// lane owns k = lane*8..+7 (+256 per extra chunk) for every row, so its weights live in registers.
+template <int OUT, int KCH>
+__global__ void k_thin_fwd(int n, const bf16* __restrict__ X, int ld, const float* __restrict__ W,
                            const float* __restrict__ bias, float* __restrict__ out) {
-  extern __shared__ float sWt[];   // [OUT][width]
-  for (int i = threadIdx.x; i < OUT * width; i += blockDim.x) sWt[i] = W[i];
-  __syncthreads();
-  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int width = KCH * 256;
+  const int lane = threadIdx.x & 31;
+  float w[KCH][OUT][8];
+#pragma unroll
+  for (int c = 0; c < KCH; ++c)
+#pragma unroll
+    for (int o = 0; o < OUT; ++o)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[c][o][e] = W[o * width + c * 256 + lane * 8 + e];
+  float bo[OUT];
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) bo[o] = bias[o];
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int row = warp; row < n; row += nwarps) {
     float acc[OUT];
 #pragma unroll
     for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
-    for (int k = lane * 8; k < width; k += 256) {
-      uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + k);
+#pragma unroll
+    for (int c = 0; c < KCH; ++c) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + c * 256 + lane * 8);
       const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+        const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) acc[o] = fmaf(xv, sWt[o * width + k + e], acc[o]);
+        for (int o = 0; o < OUT; ++o) acc[o] = fmaf(xv, w[c][o][e], acc[o]);
       }
     }
 #pragma unroll
     for (int o = 0; o < OUT; ++o) acc[o] = warp_sum(acc[o]);
     if (lane == 0) {
-#pragma unroll
-      for (int o = 0; o < 4; ++o) out[(size_t)row * 4 + o] = o < OUT ? acc[o] + bias[o] : 0.f;
+      float4 r4 = make_float4(acc[0] + bo[0], OUT > 1 ? acc[OUT > 1 ? 1 : 0] + bo[OUT > 1 ? 1 : 0] : 0.f,
+                              OUT > 2 ? acc[OUT > 2 ? 2 : 0] + bo[OUT > 2 ? 2 : 0] : 0.f, 0.f);
+      *reinterpret_cast<float4*>(out + (size_t)row * 4) = r4;
     }
   }
 }
 
-// dY_prev[row,k] = (sum_o dl[row,o] W[o,k]) * (X[row,k] > 0)     (bf16 out)
+// dY_prev[row,k] = (sum_o dl[row,o] W[o,k]) * (X[row,k] > 0)     (bf16 out); thread owns a fixed k-octet
 template <int OUT>
 __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const float* __restrict__ W,
                           const bf16* __restrict__ X, int ld, bf16* __restrict__ dY, int ldy) {
-  extern __shared__ float sWt[];
-  for (int i = threadIdx.x; i < OUT * width; i += blockDim.x) sWt[i] = W[i];
-  __syncthreads();
   const int per_row = width / 8;
-  long long total = (long long)n * per_row;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int row = (int)(i / per_row), k = (int)(i - (long long)row * per_row) * 8;
-    float d[OUT];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total_threads = gridDim.x * blockDim.x;         // multiple of per_row (host guarantees)
+  const int k = (tid % per_row) * 8;
+  float w[OUT][8];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) d[o] = dl[(size_t)row * 4 + o];
-    uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + k);
+  for (int o = 0; o < OUT; ++o)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[o][e] = W[o * width + k + e];
+  for (int row = tid / per_row; row < n; row += total_threads / per_row) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dl + (size_t)row * 4);
+    const float d[3] = {d4.x, d4.y, d4.z};
+    const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + k);
     const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      uint32_t hbits = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
+      const uint32_t hbits = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
       float s = 0.f;
 #pragma unroll
-      for (int o = 0; o < OUT; ++o) s = fmaf(d[o], sWt[o * width + k + e], s);
+      for (int o = 0; o < OUT; ++o) s = fmaf(d[o], w[o][e], s);
       f[e] = ((hbits & 0x8000u) == 0 && (hbits & 0x7FFFu) != 0) ? s : 0.f;
     }
     *reinterpret_cast<uint4*>(dY + (size_t)row * ldy + k) =
@@ -163,11 +177,12 @@ __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const 
   }
 }
 
-// dW[o,k] += sum_row dl[row,o] X[row,k] ; db[o] += sum_row dl[row,o]        (fp32 atomics, W layout [OUT, ldw])
+// dW[o,k] += sum_row dl[row,o] X[row,k] ; db[o] += sum_row dl[row,o]   (block = (width/8, 8); smem reduce over y;
+// one fp32 atomic per (o,k) per block)
 template <int OUT>
 __global__ void k_thin_dw(int n, int width, const float* __restrict__ dl, const bf16* __restrict__ X, int ld,
                           float* __restrict__ dW, int ldw, float* __restrict__ db, int rows_per_block) {
-  // thread t owns 8 consecutive k (width/8 threads used per row-slice); blockDim.y slices of rows
+  extern __shared__ float red[];      // [blockDim.y][OUT*width + OUT]
   const int kq = threadIdx.x * 8;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
   float acc[OUT][8];
@@ -176,60 +191,68 @@ __global__ void k_thin_dw(int n, int width, const float* __restrict__ dl, const 
   for (int o = 0; o < OUT; ++o) { bacc[o] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[o][e] = 0.f; }
-  if (kq < width) {
-    for (int row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
-      uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + kq);
-      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
-      float d[OUT];
-#pragma unroll
-      for (int o = 0; o < OUT; ++o) { d[o] = dl[(size_t)row * 4 + o]; bacc[o] += d[o]; }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
-#pragma unroll
-        for (int o = 0; o < OUT; ++o) acc[o][e] = fmaf(d[o], xv, acc[o][e]);
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < OUT; ++o) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&dW[(size_t)o * ldw + kq + e], acc[o][e]);
-      if (threadIdx.x == 0) atomicAdd(&db[o], bacc[o]);
-    }
-  }
-}
-
-// db[j] += sum_rows dY[row, j]  (bf16 in)
-__global__ void k_colsum_bf16(int n, int width, const bf16* __restrict__ dY, int ld, float* __restrict__ db, int rows_per_block) {
-  // blockDim = (width/8, R): thread (tx,ty) sums 8 columns over rows ty, ty+R, ...
-  __shared__ float red[8][512 + 8];
-  const int kq = threadIdx.x * 8;
-  const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
-  float acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 2
   for (int row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
-    uint4 raw = *reinterpret_cast<const uint4*>(dY + (size_t)row * ld + kq);
+    const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + kq);
+    const float4 d4 = *reinterpret_cast<const float4*>(dl + (size_t)row * 4);
+    const float d[3] = {d4.x, d4.y, d4.z};
     const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
-  }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) red[threadIdx.y][kq + e] = acc[e];
-  __syncthreads();
-  if (threadIdx.y == 0) {
+    for (int o = 0; o < OUT; ++o) bacc[o] += d[o];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float s = 0.f;
-      for (int y = 0; y < (int)blockDim.y; ++y) s += red[y][kq + e];
-      atomicAdd(&db[kq + e], s);
+      const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) acc[o][e] = fmaf(d[o], xv, acc[o][e]);
     }
+  }
+  const int stride = OUT * width + OUT;
+  float* mine = red + threadIdx.y * stride;
+#pragma unroll
+  for (int o = 0; o < OUT; ++o) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mine[o * width + kq + e] = acc[o][e];
+    if (threadIdx.x == 0) mine[OUT * width + o] = bacc[o];
+  }
+  __syncthreads();
+  const int t = threadIdx.y * blockDim.x + threadIdx.x;
+  for (int i = t; i < stride; i += blockDim.x * blockDim.y) {
+    float ssum = 0.f;
+    for (int y = 0; y < (int)blockDim.y; ++y) ssum += red[y * stride + i];
+    if (i < OUT * width) atomicAdd(&dW[(size_t)(i / width) * ldw + (i % width)], ssum);
+    else atomicAdd(&db[i - OUT * width], ssum);
   }
 }
 
-__global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, float* __restrict__ out) {
+static __global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, float* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
+}
+
+// table-driven (un)packing: one launch for every layer of both networks
+struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed
+constexpr int kMaxPack = 48;
+struct PackTable { PackEntry e[kMaxPack]; int n; };
+static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
+  const PackEntry& E = t.e[blockIdx.y];
+  const int tot = E.prow * E.pcol;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+    int pr = i / E.pcol, pc = i - pr * E.pcol;
+    int r = E.mode == 2 ? pc : pr, c = E.mode == 2 ? pr : pc;
+    float v = (r < E.rows && c < E.cols) ? E.src[(size_t)r * E.cols + c] : 0.f;
+    if (E.mode == 0) reinterpret_cast<float*>(E.dst)[i] = v;
+    else reinterpret_cast<bf16*>(E.dst)[i] = __float2bfloat16(v);
+  }
+}
+struct UnpackEntry { const float* src; float* dst; int rows, cols, pcol; };
+struct UnpackTable { UnpackEntry e[kMaxPack]; int n; };
+static __global__ void k_unpack_table(const __grid_constant__ UnpackTable t) {
+  const UnpackEntry& E = t.e[blockIdx.y];
+  const int tot = E.rows * E.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
+    int r = i / E.cols, c = i - r * E.cols;
+    E.dst[i] = E.src[(size_t)r * E.pcol + c];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ state
@@ -253,18 +276,17 @@ struct BfChain {
   int ld[MARF_MAX_LAYERS + 1] = {};
   CUtensorMap tmAct128[MARF_MAX_LAYERS + 1];   // box {64,128}: GEMM A loads / epilogue stores / mask loads
   CUtensorMap tmAct64[MARF_MAX_LAYERS + 1];    // box {64,64}: dW loads
+  bf16* dY[MARF_MAX_LAYERS] = {};         // dY[l]: gradient wrt the output of layer l [chunk, np(l)] (kept for the dW pass)
+  CUtensorMap tmDY128[MARF_MAX_LAYERS], tmDY64[MARF_MAX_LAYERS];
   float* logits = nullptr;                // [chunk,4] fp32
   float* dlogits = nullptr;               // [chunk,4] fp32
-  Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias, packing)
+  Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
 };
 
 struct Bf16State {
   EncodeTiledFn encode = nullptr;
   BfChain img, msk;
-  bf16* dY[2] = {nullptr, nullptr};       // ping-pong gradient activations [chunk, max_ld]
-  CUtensorMap tmDY128[2][8], tmDY64[2][8];   // per distinct ld (index = ld/64 - 1)
-  int max_ld = 0;
   float* dX0 = nullptr;                   // [chunk, 64] fp32
   int num_sms = 148;
 };
@@ -309,6 +331,8 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
       if (rc) return rc;
     } else if (l != F.n - 1) {
       return fail(h, MARF_ERR_UNSUPPORTED, "bf16: thin hidden layers are not supported");
+    } else if (L.k_in != 256 && L.k_in != 512) {
+      return fail(h, MARF_ERR_UNSUPPORTED, "bf16: the output layer must read 256 or 512 features");
     }
   }
   B.ld[F.n] = 4;
@@ -319,11 +343,32 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     if (rc) return rc;
     rc = make_tmap(h, S, &B.tmAct64[l], B.act[l], h->chunk, B.ld[l], 64);
     if (rc) return rc;
-    if (l >= 1) S->max_ld = std::max(S->max_ld, B.ld[l]);
+    if (l < F.n - 1) {
+      B.dY[l] = (bf16*)ws_alloc(h, (size_t)h->chunk * B.L[l].np * 2);
+      if (!B.dY[l]) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (dY)");
+      rc = make_tmap(h, S, &B.tmDY128[l], B.dY[l], h->chunk, B.L[l].np, 128);
+      if (rc) return rc;
+      rc = make_tmap(h, S, &B.tmDY64[l], B.dY[l], h->chunk, B.L[l].np, 64);
+      if (rc) return rc;
+    }
   }
   B.logits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
   B.dlogits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
   if (!B.logits || !B.dlogits) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (logits)");
+  return MARF_OK;
+}
+
+static int set_tc_attrs(marf_handle* h) {
+  const int big = 232448;
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
+  BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1 * 512 + 1) * 4));
   return MARF_OK;
 }
 
@@ -346,28 +391,9 @@ int bf16_create(marf_handle* h) {
     rc = build_bf_chain(h, S, S->msk, h->msk, false);
     if (rc) return rc;
   }
-  for (int i = 0; i < 2; ++i) {
-    S->dY[i] = (bf16*)ws_alloc(h, (size_t)h->chunk * S->max_ld * 2);
-    if (!S->dY[i]) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (dY)");
-    for (int w = 1; w * 64 <= S->max_ld && w <= 8; ++w) {
-      rc = make_tmap(h, S, &S->tmDY128[i][w - 1], S->dY[i], h->chunk, w * 64, 128);
-      if (rc) return rc;
-      rc = make_tmap(h, S, &S->tmDY64[i][w - 1], S->dY[i], h->chunk, w * 64, 64);
-      if (rc) return rc;
-    }
-  }
   S->dX0 = (float*)ws_alloc(h, (size_t)h->chunk * 64 * sizeof(float));
   if (!S->dX0) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (dX0)");
-  // opt in to the large dynamic shared memory the kernels need
-  const int big = 232448;
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  return MARF_OK;
+  return set_tc_attrs(h);
 }
 
 void bf16_destroy(marf_handle* h) {
@@ -399,31 +425,29 @@ static int launch_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int l, int ro
   return MARF_OK;
 }
 
-// dY_{l-1} = (dY_l W_l) * (act[l] > 0), l >= 1;  in: dY[cur] (ld = np of layer l), out: dY[cur^1] (ld = kp of layer l)
-static int launch_dx(marf_handle* h, cudaStream_t st, BfChain& B, int l, int rows, int cur) {
+// dY[l-1] = (dY[l] W_l) * (act[l] > 0), l >= 1
+static int launch_dx(marf_handle* h, cudaStream_t st, BfChain& B, int l, int rows) {
   Bf16State* S = h->bf16;
   BfLayer& L = B.L[l];
   tc::GemmParams p{};
   p.n_tiles = rows / 128;
   p.k_chunks = L.np / 64;                    // contraction over the layer's outputs
-  int n_total = L.kp;                        // produces the layer's (padded) inputs
+  int n_total = L.kp;                        // produces the layer's (padded) inputs = np of layer l-1
   int n_tile = std::min(n_total, 256);
   if (n_total % n_tile) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: input width must tile by 256/128/64");
   dim3 grid(std::min(p.n_tiles, std::max(1, S->num_sms / (n_total / n_tile))), n_total / n_tile);
   int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
-  const CUtensorMap& tmIn = S->tmDY128[cur][L.np / 64 - 1];
-  const CUtensorMap& tmOut = S->tmDY128[cur ^ 1][L.kp / 64 - 1];
   if (n_tile == 256)
-    tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tmIn, L.tmWt, tmOut, B.tmAct128[l], p);
+    tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[l], L.tmWt, B.tmDY128[l - 1], B.tmAct128[l], p);
   else if (n_tile == 128)
-    tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tmIn, L.tmWt, tmOut, B.tmAct128[l], p);
+    tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[l], L.tmWt, B.tmDY128[l - 1], B.tmAct128[l], p);
   else
     return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: unsupported tile");
   BF_LAUNCH(h);
   return MARF_OK;
 }
 
-static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain& B, int rows, int cur) {
+static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain& B, int rows) {
   Bf16State* S = h->bf16;
   BfLayer& L = B.L[0];
   if (L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX0: encoded input must fit 64 columns");
@@ -435,55 +459,55 @@ static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain& B, int rows, int
   p.n_store = pad4(L.k_in);
   dim3 grid(std::min(p.n_tiles, S->num_sms), 1);
   int smem = tc::gemm_smem(64, p.k_chunks, false).total + 1024;
-  const CUtensorMap& tmIn = S->tmDY128[cur][L.np / 64 - 1];
-  tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(tmIn, L.tmWt, tmIn, tmIn, p);
+  tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[0], L.tmWt, B.tmDY128[0], B.tmDY128[0], p);
   BF_LAUNCH(h);
   return MARF_OK;
 }
 
-// dW_l += dY_l^T act[l], db_l += colsum(dY_l);  dY_l in dY[cur] with ld = np
-static int launch_dw(marf_handle* h, cudaStream_t st, BfChain& B, int l, int rows, int cur) {
+// all dW / db of the tensor-core layers of the given chains: one launch per N-tile width
+static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
   Bf16State* S = h->bf16;
-  BfLayer& L = B.L[l];
-  Chain& F = *B.f32;
-  tc::DwParams p{};
-  p.rows = rows;
-  p.m_halves = (L.k_out + 127) / 128;
-  p.m_valid = L.k_out;
-  p.n_valid = L.k_in;
-  p.dW = F.gWp[l];
-  p.ld_w = F.ld_in[l];
-  int n_tile = L.kp >= 256 ? 256 : 64;
-  if (n_tile == 64 && L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: input width must be 64 or >= 256");
-  int n_tiles_n = (L.kp + n_tile - 1) / n_tile;
-  int ctas = std::max(1, S->num_sms / n_tiles_n);
-  int per = (int)round_up((rows + ctas - 1) / ctas, 64);
-  p.rows_per_cta = std::max(per, 64);
-  ctas = (rows + p.rows_per_cta - 1) / p.rows_per_cta;
-  dim3 grid(ctas, n_tiles_n);
-  int stage = (p.m_halves * 2 + n_tile / 64) * tc::kDwSlab;
-  int smem = tc::kDwStages * stage + 256 + 1024;
-  const CUtensorMap& tmDY = S->tmDY64[cur][L.np / 64 - 1];
-  if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(tmDY, B.tmAct64[l], p);
-  else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(tmDY, B.tmAct64[l], p);
-  BF_LAUNCH(h);
-  {
-    int rpb = std::max(512, (rows + 295) / 296);
-    dim3 block(L.np / 8, std::min(8, std::max(1, 256 / (L.np / 8))));
-    k_colsum_bf16<<<(rows + rpb - 1) / rpb, block, 0, st>>>(rows, L.np, S->dY[cur], L.np, F.gbp[l], rpb);
-    BF_LAUNCH(h);
-  }
-  return MARF_OK;
-}
-
-static int pack_bf_chain(marf_handle* h, cudaStream_t st, BfChain& B, const float* const* W) {
-  for (int l = 0; l < B.n; ++l) {
-    BfLayer& L = B.L[l];
-    if (L.thin) continue;
-    int tot = L.np * L.kp;
-    k_pack_bf16<<<(tot + 255) / 256, 256, 0, st>>>(W[l], L.k_out, L.k_in, L.Wk, L.np, L.kp, 0);
-    BF_LAUNCH(h);
-    k_pack_bf16<<<(tot + 255) / 256, 256, 0, st>>>(W[l], L.k_out, L.k_in, L.Wt, L.kp, L.np, 1);
+  for (int pass = 0; pass < 2; ++pass) {          // pass 0: N_TILE=256 jobs, pass 1: N_TILE=64 jobs
+    const int n_tile = pass == 0 ? 256 : 64;
+    tc::DwJobs jobs;
+    int nj = 0;
+    int max_stage = 0;
+    for (int ci = 0; ci < n_chains; ++ci) {
+      BfChain& B = *chains[ci];
+      Chain& F = *B.f32;
+      for (int l = 0; l < B.n - 1; ++l) {
+        BfLayer& L = B.L[l];
+        const int lt = L.kp >= 256 ? 256 : 64;
+        if (lt == 64 && L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: input width must be 64 or >= 256");
+        if (lt != n_tile) continue;
+        const int n_tiles_n = (L.kp + n_tile - 1) / n_tile;
+        for (int t = 0; t < n_tiles_n; ++t) {
+          if (nj >= tc::kDwMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
+          tc::DwJob& J = jobs.j[nj++];
+          J.tmDY = B.tmDY64[l];
+          J.tmX = B.tmAct64[l];
+          J.rows = rows;
+          J.m_halves = (L.k_out + 127) / 128;
+          J.m_valid = L.k_out;
+          J.n_valid = L.k_in;
+          J.n0 = t * n_tile;
+          J.ld_w = F.ld_in[l];
+          J.do_bias = t == 0;
+          J.dW = F.gWp[l];
+          J.db = F.gbp[l];
+          max_stage = std::max(max_stage, (J.m_halves * 2 + n_tile / 64) * tc::kDwSlab);
+        }
+      }
+    }
+    if (nj == 0) continue;
+    int ctas = std::max(1, S->num_sms / nj);
+    int per = std::max((int)round_up((rows + ctas - 1) / ctas, 64), 64);
+    ctas = (rows + per - 1) / per;
+    for (int i = 0; i < nj; ++i) jobs.j[i].rows_per_cta = per;
+    dim3 grid(ctas, nj);
+    int smem = tc::kDwStages * max_stage + 256 + 1024;
+    if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(jobs);
+    else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(jobs);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -491,38 +515,38 @@ static int pack_bf_chain(marf_handle* h, cudaStream_t st, BfChain& B, const floa
 
 static int thin_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* W, const float* bias) {
   int l = B.n - 1;
-  int width = B.L[l].k_in;
-  int out = B.L[l].k_out;
-  int smem = out * width * sizeof(float);
+  int width = B.L[l].k_in, out = B.L[l].k_out;
   int blocks = std::min((rows + 7) / 8, h->bf16->num_sms * 8);
-  if (out == 3) k_thin_fwd<3><<<blocks, 256, smem, st>>>(rows, width, B.act[l], B.ld[l], W, bias, B.logits);
-  else if (out == 1) k_thin_fwd<1><<<blocks, 256, smem, st>>>(rows, width, B.act[l], B.ld[l], W, bias, B.logits);
-  else return fail(h, MARF_ERR_UNSUPPORTED, "bf16: output layer must be 3- or 1-wide");
+  if (out == 3 && width == 256) k_thin_fwd<3, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 3 && width == 512) k_thin_fwd<3, 2><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 1 && width == 256) k_thin_fwd<1, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 1 && width == 512) k_thin_fwd<1, 2><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else return fail(h, MARF_ERR_UNSUPPORTED, "bf16: output layer must be 3- or 1-wide over 256/512 features");
   BF_LAUNCH(h);
   return MARF_OK;
 }
 
-// last layer backward: dW/db (fp32 atomics into the padded fp32 twin) and dY of the previous layer -> dY[0]
+// last layer backward: dW/db (fp32 atomics into the padded fp32 twin) and dY of the previous layer
 static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* W) {
   Bf16State* S = h->bf16;
   Chain& F = *B.f32;
   int l = B.n - 1;
   int width = B.L[l].k_in, out = B.L[l].k_out;
-  int smem = out * width * sizeof(float);
-  int rpb = std::max(256, (rows + 591) / 592);
-  dim3 blk(width / 8, std::max(1, 256 / (width / 8)));
+  int rpb = std::max(256, (rows + 2 * S->num_sms - 1) / (2 * S->num_sms));
+  dim3 blk(width / 8, 8);
   int nblk = (rows + rpb - 1) / rpb;
-  int ldprev = B.ld[l];
-  long long tot = (long long)rows * (width / 8);
-  int dxblocks = (int)std::min<long long>((tot + 255) / 256, (long long)S->num_sms * 16);
+  int smem = 8 * (out * width + out) * sizeof(float);
+  int per_row = width / 8;
+  int dxthreads = 256 / per_row * per_row;             // threads per block: multiple of per_row
+  int dxblocks = std::min((rows * per_row + dxthreads - 1) / dxthreads, S->num_sms * 16);
   if (out == 3) {
-    k_thin_dw<3><<<nblk, blk, 0, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+    k_thin_dw<3><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<3><<<dxblocks, 256, smem, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], S->dY[0], ldprev);
+    k_thin_dx<3><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], B.dY[l - 1], B.L[l - 1].np);
   } else {
-    k_thin_dw<1><<<nblk, blk, 0, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+    k_thin_dw<1><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<1><<<dxblocks, 256, smem, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], S->dY[0], ldprev);
+    k_thin_dx<1><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], B.dY[l - 1], B.L[l - 1].np);
   }
   BF_LAUNCH(h);
   return MARF_OK;
@@ -536,22 +560,74 @@ static int bf_chain_forward(marf_handle* h, cudaStream_t st, BfChain& B, int row
   return thin_fwd(h, st, B, rows, Wlast, blast);
 }
 
-static int bf_chain_backward(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* Wlast) {
-  int rc = thin_bwd(h, st, B, rows, Wlast);      // -> dY[0] holds dY of layer n-2
+// dX chain only (dY[l] for every tensor-core layer stays resident for launch_dw_all)
+static int bf_chain_backward_dx(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* Wlast) {
+  int rc = thin_bwd(h, st, B, rows, Wlast);      // -> dY[n-2]
   if (rc) return rc;
-  int cur = 0;
-  for (int l = B.n - 2; l >= 0; --l) {
-    rc = launch_dw(h, st, B, l, rows, cur);
+  for (int l = B.n - 2; l >= 1; --l) {
+    rc = launch_dx(h, st, B, l, rows);
     if (rc) return rc;
-    if (l > 0) {
-      rc = launch_dx(h, st, B, l, rows, cur);
-      if (rc) return rc;
-      cur ^= 1;
-    } else if (B.need_dx0) {
-      rc = launch_dx0(h, st, B, rows, cur);
-      if (rc) return rc;
+  }
+  if (B.need_dx0) rc = launch_dx0(h, st, B, rows);
+  return rc;
+}
+
+// one launch: bias (fp32) + bf16 forward / transposed weights of every tensor-core layer
+static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
+  Bf16State* S = h->bf16;
+  PackTable t;
+  t.n = 0;
+  int max_tot = 0;
+  auto add = [&](const float* src, void* dst, int rows, int cols, int prow, int pcol, int mode) {
+    PackEntry& e = t.e[t.n++];
+    e.src = src; e.dst = dst; e.rows = rows; e.cols = cols; e.prow = prow; e.pcol = pcol; e.mode = mode;
+    max_tot = std::max(max_tot, prow * pcol);
+  };
+  BfChain* chains[2] = {&S->img, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? &S->msk : nullptr};
+  const float* const* Ws[2] = {io->mlp_w, io->mask_w};
+  const float* const* bs[2] = {io->mlp_b, io->mask_b};
+  for (int ci = 0; ci < 2; ++ci) {
+    if (!chains[ci]) continue;
+    BfChain& B = *chains[ci];
+    Chain& F = *B.f32;
+    for (int l = 0; l < B.n; ++l) {
+      if (!Ws[ci][l] || !bs[ci][l]) return fail(h, MARF_ERR_INVALID, "null layer parameter");
+      if (t.n + 3 > kMaxPack) return fail(h, MARF_ERR_UNSUPPORTED, "too many layers");
+      add(bs[ci][l], F.bp[l], 1, F.k_out[l], 1, F.ld_out[l], 0);
+      if (B.L[l].thin) continue;
+      add(Ws[ci][l], B.L[l].Wk, B.L[l].k_out, B.L[l].k_in, B.L[l].np, B.L[l].kp, 1);
+      add(Ws[ci][l], B.L[l].Wt, B.L[l].k_out, B.L[l].k_in, B.L[l].kp, B.L[l].np, 2);
     }
   }
+  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
+  k_pack_table<<<grid, 256, 0, st>>>(t);
+  BF_LAUNCH(h);
+  return MARF_OK;
+}
+
+static int unpack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
+  Bf16State* S = h->bf16;
+  UnpackTable t;
+  t.n = 0;
+  int max_tot = 0;
+  BfChain* chains[2] = {&S->img, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? &S->msk : nullptr};
+  float* const* gW[2] = {io->g_mlp_w, io->g_mask_w};
+  float* const* gb[2] = {io->g_mlp_b, io->g_mask_b};
+  for (int ci = 0; ci < 2; ++ci) {
+    if (!chains[ci]) continue;
+    if (!gW[ci] || !gb[ci]) return fail(h, MARF_ERR_INVALID, "missing gradient pointers");
+    Chain& F = *chains[ci]->f32;
+    for (int l = 0; l < F.n; ++l) {
+      UnpackEntry& a = t.e[t.n++];
+      a.src = F.gWp[l]; a.dst = gW[ci][l]; a.rows = F.k_out[l]; a.cols = F.k_in[l]; a.pcol = F.ld_in[l];
+      UnpackEntry& b = t.e[t.n++];
+      b.src = F.gbp[l]; b.dst = gb[ci][l]; b.rows = 1; b.cols = F.k_out[l]; b.pcol = F.ld_out[l];
+      max_tot = std::max(max_tot, F.k_out[l] * F.k_in[l]);
+    }
+  }
+  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
+  k_unpack_table<<<grid, 256, 0, st>>>(t);
+  BF_LAUNCH(h);
   return MARF_OK;
 }
 
@@ -591,7 +667,7 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-    k_loss_stats<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, a, io->loss_sums);
+    k_loss_stats<<<std::min((rg.padded + 255) / 256, 592), 256, 0, st>>>(h->geo, rg, a, io->loss_sums);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -614,34 +690,30 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.dmlogits = implicit ? S->msk.dlogits : nullptr; ga.dmld = 4;
   k_loss_grad<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, ga, h->coef);
   BF_LAUNCH(h);
-  int rc = bf_chain_backward(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
+  int rc = bf_chain_backward_dx(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
   if (rc) return rc;
-  k_encode_backward<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, h->Hm, S->dX0, 64, h->G);
+  k_encode_backward<<<(rg.padded + 255) / 256, 256, 0, st>>>(h->geo, rg, h->Hm, S->dX0, 64, h->G);
   BF_LAUNCH(h);
   if (implicit) {
-    rc = bf_chain_backward(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
+    rc = bf_chain_backward_dx(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
     if (rc) return rc;
   }
-  return MARF_OK;
+  BfChain* chains[2] = {&S->img, &S->msk};
+  return launch_dw_all(h, st, chains, implicit ? 2 : 1, rg.padded);
 }
 
 // shared with api.cu
-int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st);
+int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32);
 int engine_edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st);
 int engine_begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st);
-int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st);
+int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack);
 
 int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
-  Bf16State* S = h->bf16;
   const marf_config& c = h->cfg;
-  int rc = engine_begin_step(h, io, st);          // fp32 packing (bias), H matrices, schedule, data caches
+  int rc = engine_begin_step(h, io, st, false);   // H matrices, schedule, data caches
   if (rc) return rc;
-  rc = pack_bf_chain(h, st, S->img, io->mlp_w);
+  rc = pack_all(h, st, io);
   if (rc) return rc;
-  if (c.mask_mode == MARF_MASK_IMPLICIT) {
-    rc = pack_bf_chain(h, st, S->msk, io->mask_w);
-    if (rc) return rc;
-  }
   BF_TRY(h, cudaMemsetAsync(io->loss_sums, 0, MARF_N_SUMS * sizeof(double), st));
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     rc = bf_forward_chunk(h, io, st, ci, true);
@@ -670,7 +742,9 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
     if (rc) return rc;
   }
   h->acts_valid = false;
-  return engine_finish_backward(h, io, st);
+  rc = engine_finish_backward(h, io, st, false);
+  if (rc) return rc;
+  return unpack_all(h, st, io);
 }
 
 int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
@@ -686,7 +760,7 @@ int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
 //   mode 0: out[rows,N] = relu(A[rows,K] W[N,K]^T + aux[N])          (k_tc_gemm, EPI_BIAS_RELU; bf16-rounded output)
 //   mode 1: out[rows,N] = (A W^T) * (aux[rows,N] > 0)                 (k_tc_gemm, EPI_RELU_MASK; bf16-rounded output)
 //   mode 2: out[rows,64] = A[rows,K] W[64,K]^T                        (k_tc_gemm, EPI_PLAIN_F32)
-//   mode 3: out[N(out),K(in)] = A[rows,N]^T aux[rows,K]               (k_tc_dw; A = dY, aux = X)
+//   mode 3: out[N(out),K(in)] = A[rows,N]^T aux[rows,K], then out[N*K + o] = colsum(A)[o]   (k_tc_dw; A = dY, aux = X)
 extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, const float* A, const float* W,
                                 const float* aux, float* out, void* stream) {
   using namespace marf;
@@ -767,22 +841,27 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     if (!dA || !dAux) return MARF_ERR_CUDA;
     rc = make_tmap(&tmp, &S, &tA, dA, rows, N, 64);
     if (!rc) rc = make_tmap(&tmp, &S, &tM, dAux, rows, K, 64);
-    tc::DwParams p{};
-    p.rows = rows; p.m_halves = (N + 127) / 128; p.m_valid = N; p.n_valid = K; p.dW = out; p.ld_w = K;
     int n_tile = K >= 256 ? 256 : 64;
     if (n_tile == 64 && K != 64) return MARF_ERR_INVALID;
     if (N > 256) return MARF_ERR_INVALID;
     int n_tiles_n = (K + n_tile - 1) / n_tile;
     int ctas = std::max(1, 148 / n_tiles_n);
-    p.rows_per_cta = std::max((int)round_up((rows + ctas - 1) / ctas, 64), 64);
-    ctas = (rows + p.rows_per_cta - 1) / p.rows_per_cta;
-    cudaMemsetAsync(out, 0, (size_t)N * K * sizeof(float), st);
-    int stage = (p.m_halves * 2 + n_tile / 64) * tc::kDwSlab;
+    int per = std::max((int)round_up((rows + ctas - 1) / ctas, 64), 64);
+    ctas = (rows + per - 1) / per;
+    // out holds [N, K] weights followed by [N] bias sums
+    cudaMemsetAsync(out, 0, ((size_t)N * K + N) * sizeof(float), st);
+    tc::DwJobs jobs;
+    for (int t = 0; t < n_tiles_n; ++t) {
+      tc::DwJob& J = jobs.j[t];
+      J.tmDY = tA; J.tmX = tM; J.rows = rows; J.rows_per_cta = per; J.m_halves = (N + 127) / 128; J.m_valid = N;
+      J.n_valid = K; J.n0 = t * n_tile; J.ld_w = K; J.do_bias = t == 0; J.dW = out; J.db = out + (size_t)N * K;
+    }
+    int stage = (((N + 127) / 128) * 2 + n_tile / 64) * tc::kDwSlab;
     int smem = tc::kDwStages * stage + 256 + 1024;
     dim3 grid(ctas, n_tiles_n);
     if (!rc) {
-      if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(tA, tM, p);
-      else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(tA, tM, p);
+      if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(jobs);
+      else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(jobs);
     }
   } else {
     return MARF_ERR_INVALID;

@@ -53,44 +53,97 @@ __device__ __forceinline__ void sl3_generator(const float* h, double* A) {
   A[6] = h[6]; A[7] = h[7]; A[8] = h[5];
 }
 
-static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
-  double A[9], E[9];
-  if (warp) sl3_generator(warp + 8 * b, A);
-  else for (int i = 0; i < 9; ++i) A[i] = 0.0;
-  expm_small<3>(A, E);
-  for (int i = 0; i < 9; ++i) out9[9 * b + i] = (float)E[i];
+// Cooperative expm: N*N threads of one block, one matrix element each, fp64 in shared memory.
+// Scaling-and-squaring with a degree-12 Taylor polynomial (||A/2^s||_1 <= 0.25 -> truncation < 1e-16).
+template <int N>
+__device__ void expm_coop(double* X /*[N*N] in: A, scratch*/, double* T, double* R, int tid) {
+  const bool on = tid < N * N;
+  const int i = tid / N, j = tid % N;
+  __shared__ int s_sq;
+  if (tid == 0) {
+    double nrm = 0.0;
+    for (int c = 0; c < N; ++c) {
+      double cs = 0.0;
+      for (int r = 0; r < N; ++r) cs += fabs(X[r * N + c]);
+      nrm = fmax(nrm, cs);
+    }
+    int sq = 0;
+    while (nrm > 0.25 && sq < 60) { nrm *= 0.5; ++sq; }
+    s_sq = sq;
+  }
+  __syncthreads();
+  const int sq = s_sq;
+  if (on) {
+    X[tid] *= ldexp(1.0, -sq);
+    T[tid] = (i == j) ? 1.0 : 0.0;
+    R[tid] = T[tid];
+  }
+  __syncthreads();
+  for (int k = 1; k <= 12; ++k) {
+    double v = 0.0;
+    if (on) {
+      for (int q = 0; q < N; ++q) v += T[i * N + q] * X[q * N + j];
+      v /= (double)k;
+    }
+    __syncthreads();
+    if (on) { T[tid] = v; R[tid] += v; }
+    __syncthreads();
+  }
+  for (int s = 0; s < sq; ++s) {
+    double v = 0.0;
+    if (on) for (int q = 0; q < N; ++q) v += R[i * N + q] * R[q * N + j];
+    __syncthreads();
+    if (on) R[tid] = v;
+    __syncthreads();
+  }
 }
 
-// G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches)
+// one block (64 threads) per patch
+static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
+  __shared__ double X[9], T[9], R[9];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) {
+    if (warp) sl3_generator(warp + 8 * b, X);
+    else for (int i = 0; i < 9; ++i) X[i] = 0.0;
+  }
+  __syncthreads();
+  expm_coop<3>(X, T, R, tid);
+  if (tid < 9) out9[9 * b + tid] = (float)R[tid];
+}
+
+// G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches); one block per patch
 static __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
                                int n_local, float* __restrict__ g_warp) {
-  int bl = blockIdx.x * blockDim.x + threadIdx.x;
-  if (bl >= n_local) return;
-  int b = bl + patch_offset;
-  double A[9], M[36], E[36];
-  sl3_generator(warp + 8 * b, A);
-  for (int i = 0; i < 36; ++i) M[i] = 0.0;
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) {
-      M[i * 6 + j] = A[j * 3 + i];                 // A^T
-      M[(i + 3) * 6 + (j + 3)] = A[j * 3 + i];     // A^T
-      M[i * 6 + (j + 3)] = G[9 * bl + i * 3 + j];  // upstream
-    }
-  expm_small<6>(M, E);
-  double dA[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) dA[i * 3 + j] = E[i * 6 + (j + 3)];
-  float* o = g_warp + 8 * b;
-  o[0] = (float)dA[2];            // h1 -> A02
-  o[1] = (float)dA[5];            // h2 -> A12
-  o[2] = (float)dA[1];            // h3 -> A01
-  o[3] = (float)dA[3];            // h4 -> A10
-  o[4] = (float)(dA[0] - dA[4]);  // h5 -> A00, -A11
-  o[5] = (float)(dA[8] - dA[4]);  // h6 -> A22, -A11
-  o[6] = (float)dA[6];            // h7 -> A20
-  o[7] = (float)dA[7];            // h8 -> A21
+  __shared__ double X[36], T[36], R[36];
+  const int bl = blockIdx.x, tid = threadIdx.x;
+  const int b = bl + patch_offset;
+  if (tid == 0) {
+    double A[9];
+    sl3_generator(warp + 8 * b, A);
+    for (int i = 0; i < 36; ++i) X[i] = 0.0;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        X[i * 6 + j] = A[j * 3 + i];                 // A^T
+        X[(i + 3) * 6 + (j + 3)] = A[j * 3 + i];     // A^T
+        X[i * 6 + (j + 3)] = G[9 * bl + i * 3 + j];  // upstream
+      }
+  }
+  __syncthreads();
+  expm_coop<6>(X, T, R, tid);
+  if (tid == 0) {
+    double dA[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) dA[i * 3 + j] = R[i * 6 + (j + 3)];
+    float* o = g_warp + 8 * b;
+    o[0] = (float)dA[2];            // h1 -> A02
+    o[1] = (float)dA[5];            // h2 -> A12
+    o[2] = (float)dA[1];            // h3 -> A01
+    o[3] = (float)dA[3];            // h4 -> A10
+    o[4] = (float)(dA[0] - dA[4]);  // h5 -> A00, -A11
+    o[5] = (float)(dA[8] - dA[4]);  // h6 -> A22, -A11
+    o[6] = (float)dA[6];            // h7 -> A20
+    o[7] = (float)dA[7];            // h8 -> A21
+  }
 }
 
 // warped crop corners (warp.py:83-93): [(X0,Y0),(X0,Y1),(X1,Y1),(X1,Y0)]
@@ -195,18 +248,41 @@ static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restr
     acc[3] = dq1 * x; acc[4] = dq1 * y; acc[5] = dq1;
     acc[6] = dq2 * x; acc[7] = dq2 * y; acc[8] = dq2;
   }
-  int b0 = __shfl_sync(0xffffffffu, b, 0);
-  bool uniform = __all_sync(0xffffffffu, b == b0);
+  // reduce: warp shuffles -> per-warp slots in shared memory -> one fp64 atomic per (patch, entry) per block
+  __shared__ float slot[8][9];
+  __shared__ int slot_b[8];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  int b0 = __shfl_sync(0xffffffffu, b, 0);   // lane 0 is valid whenever any lane of the warp is (t ascending)
+  bool uniform = __all_sync(0xffffffffu, b == b0 || b < 0);
   if (uniform) {
-    if (b0 < 0) return;
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-      float s = warp_sum(acc[i]);
-      if ((threadIdx.x & 31) == 0) atomicAdd(&G[9 * b0 + i], (double)s);
+      float sacc = warp_sum(acc[i]);
+      if (lane == 0) slot[wid][i] = sacc;
     }
-  } else if (valid) {
+    if (lane == 0) slot_b[wid] = b0;
+  } else {
+    if (lane == 0) slot_b[wid] = -1;
+    if (valid) {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) atomicAdd(&G[9 * b + i], (double)acc[i]);
+      for (int i = 0; i < 9; ++i) atomicAdd(&G[9 * b + i], (double)acc[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    int cur = -1;
+    double tot = 0.0;
+    for (int w = 0; w < nw; ++w) {
+      int wb = slot_b[w];
+      if (wb < 0) continue;
+      if (wb != cur) {
+        if (cur >= 0) atomicAdd(&G[9 * cur + threadIdx.x], tot);
+        cur = wb;
+        tot = 0.0;
+      }
+      tot += (double)slot[w][threadIdx.x];
+    }
+    if (cur >= 0) atomicAdd(&G[9 * cur + threadIdx.x], tot);
   }
 }
 
@@ -430,12 +506,26 @@ struct LossArgs {
   float* mask_pred;            // optional [n_total]
 };
 
+__device__ __forceinline__ void block_sum_atomic(double v, double* dst, double* red /*[32]*/) {
+  // all threads of the block call this; blockDim.x multiple of 32, <= 1024
+  v = warp_sum(v);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0 && t != 0.0) atomicAdd(dst, t);
+  }
+}
+
 static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__ sums) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[32];
   double s_rgb = 0, n_rgb = 0, s_mask = 0, n_mask = 0, bad = 0;
-  if (t < rg.count) {
+  const long long per = (long long)g.rows * g.w;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < rg.count; t += gridDim.x * blockDim.x) {
     long long i = rg.first + t;
-    long long per = (long long)g.rows * g.w;
     long long b = i / per, rem = i - b * per;
     float m = 1.f;
     if (a.mask_mode == MARF_MASK_DISK) m = a.masks[i];
@@ -443,9 +533,9 @@ static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __res
       m = sigmoidf_acc(a.mlogits[(size_t)t * a.mld]);
       if (a.mask_pred) a.mask_pred[i] = m;
       float om = 1.f - m;
-      s_mask = (double)(om * om);
+      s_mask += (double)(om * om);
     }
-    n_mask = 1.0;
+    n_mask += 1.0;
     float acc = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -453,22 +543,18 @@ static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __res
       if (a.rgb_pred) a.rgb_pred[i * 3 + c] = p;
       float d = (p - a.rgb[(b * 3 + c) * per + rem]) * m;
       acc += d * d;
-      if (!isfinite(p)) bad = 1.0;
+      if (!isfinite(p)) bad += 1.0;
     }
-    s_rgb = (double)acc;
-    n_rgb = 3.0 * (double)m;
+    s_rgb += (double)acc;
+    n_rgb += 3.0 * (double)m;
   }
-  s_rgb = warp_sum(s_rgb); n_rgb = warp_sum(n_rgb); s_mask = warp_sum(s_mask); n_mask = warp_sum(n_mask);
-  bad = warp_sum(bad);
-  if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&sums[MARF_S_RGB], s_rgb);
-    atomicAdd(&sums[MARF_N_RGB], n_rgb);
-    if (a.mask_mode == MARF_MASK_IMPLICIT) {
-      atomicAdd(&sums[MARF_S_MASK], s_mask);
-      atomicAdd(&sums[MARF_N_MASK], n_mask);
-    }
-    if (bad != 0.0) atomicAdd(&sums[MARF_NONFINITE], bad);
+  block_sum_atomic(s_rgb, &sums[MARF_S_RGB], red);
+  block_sum_atomic(n_rgb, &sums[MARF_N_RGB], red);
+  if (a.mask_mode == MARF_MASK_IMPLICIT) {
+    block_sum_atomic(s_mask, &sums[MARF_S_MASK], red);
+    block_sum_atomic(n_mask, &sums[MARF_N_MASK], red);
   }
+  block_sum_atomic(bad, &sums[MARF_NONFINITE], red);
 }
 
 // static mask sum (disk masks): N_RGB = 3 * sum m over the local shard

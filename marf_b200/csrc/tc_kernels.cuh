@@ -227,28 +227,39 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 }
 
 // ================================================================================================
-// dW[out, in] += sum over pixel rows of dY[row, out] * X[row, in]
+// dW[out, in] += sum over pixel rows of dY[row, out] * X[row, in];  db[out] += sum over rows of dY[row, out]
+// One launch covers several layers ("jobs", blockIdx.y); blockIdx.x splits the pixel rows of a job.
+// While the MMA warp streams the stages, the four epilogue warps read the dY stage from SMEM and keep the
+// bias-gradient column sums in registers (no extra pass over dY in HBM).
 // ================================================================================================
-struct DwParams {
+struct DwJob {
+  CUtensorMap tmDY;     // box {64,64} over dY [rows, out]
+  CUtensorMap tmX;      // box {64,64} over X  [rows, in]
   int rows;             // padded pixel rows (multiple of 64)
   int rows_per_cta;     // multiple of 64
   int m_halves;         // ceil(out / 128)
   int m_valid;          // out features
   int n_valid;          // in features
-  float* dW;            // [out, ld_w] fp32, accumulated with red.add
+  int n0;               // first input column of this job's N tile
   int ld_w;
+  int do_bias;          // accumulate db (only one N tile per layer does)
+  float* dW;            // [out, ld_w] fp32, accumulated with red.add
+  float* db;            // [out] fp32
 };
+constexpr int kDwMaxJobs = 8;
+struct DwJobs { DwJob j[kDwMaxJobs]; };
+
 constexpr int kDwStages = 3;
 constexpr int kDwRows = 64;                 // pixel rows per stage
 constexpr int kDwSlab = kDwRows * 128;      // [64 rows x 64 cols] bf16
 
 template <int N_TILE>
-__global__ void __launch_bounds__(kThreads, 1)
-k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, DwParams p) {
+__global__ void __launch_bounds__(kThreads, 1) k_tc_dw(const __grid_constant__ DwJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const DwJob& J = jobs.j[blockIdx.y];
   constexpr int kBSlabs = N_TILE / 64;
-  const int a_slabs = p.m_halves * 2;
+  const int a_slabs = J.m_halves * 2;
   const int stage_bytes = (a_slabs + kBSlabs) * kDwSlab;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * stage_bytes);
   uint64_t* full = bars;
@@ -258,15 +269,14 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtens
   const uint32_t tmem_cols = 512;   // m_halves * N_TILE <= 512
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * N_TILE;
-  const int row_begin = blockIdx.x * p.rows_per_cta;
-  const int row_end = min(p.rows, row_begin + p.rows_per_cta);
+  const int row_begin = blockIdx.x * J.rows_per_cta;
+  const int row_end = min(J.rows, row_begin + J.rows_per_cta);
   const int n_iter = row_begin < row_end ? (row_end - row_begin) / kDwRows : 0;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmDY);
-    prefetch_tmap(&tmX);
-    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    prefetch_tmap(&J.tmDY);
+    prefetch_tmap(&J.tmX);
+    for (int s = 0; s < kDwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -285,8 +295,8 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtens
           mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + s * stage_bytes;
           const int row = row_begin + it * kDwRows;
-          for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &tmDY, i * 64, row, &full[s]);
-          for (int i = 0; i < kBSlabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &tmX, n0 + i * 64, row, &full[s]);
+          for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &J.tmDY, i * 64, row, &full[s]);
+          for (int i = 0; i < kBSlabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &J.tmX, J.n0 + i * 64, row, &full[s]);
         }
       }
     } else if (warp == 1) {
@@ -300,7 +310,7 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtens
 #pragma unroll
           for (int ks = 0; ks < kDwRows / 16; ++ks) {
             const uint64_t db = smem_desc_sw128(st + a_slabs * kDwSlab + ks * 2048, kDwSlab, 1024);
-            for (int mh = 0; mh < p.m_halves; ++mh) {
+            for (int mh = 0; mh < J.m_halves; ++mh) {
               const uint64_t da = smem_desc_sw128(st + mh * 2 * kDwSlab + ks * 2048, kDwSlab, 1024);
               umma_bf16(tmem_base + mh * N_TILE, da, db, idesc, (it | ks) != 0);
             }
@@ -312,20 +322,45 @@ k_tc_dw(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtens
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;
+      // ---- bias gradient: warp q sums the 64 out-columns of dY slab q (if present) over the stage's 64 rows
+      float bs0 = 0.f, bs1 = 0.f;
+      const bool bias_warp = J.do_bias && q < a_slabs;
+      for (int it = 0; it < n_iter; ++it) {
+        const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
+        mbar_wait(&full[s], ph);
+        if (bias_warp) {
+          const uint8_t* slab = smem + s * stage_bytes + q * kDwSlab;
+#pragma unroll 8
+          for (int k = 0; k < kDwRows; ++k) {
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)k & 7)) << 4) +
+                                                                  ((uint32_t)lane & 3) * 4);
+            bs0 += __uint_as_float(w << 16);
+            bs1 += __uint_as_float(w & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      if (bias_warp) {
+        const int col = q * 64 + lane * 2;
+        if (col < J.m_valid) atomicAdd(&J.db[col], bs0);
+        if (col + 1 < J.m_valid) atomicAdd(&J.db[col + 1], bs1);
+      }
+      // ---- dW accumulators -> global
       mbar_wait(done, 0);
       tc_fence_after();
-      for (int mh = 0; mh < p.m_halves; ++mh) {
+      for (int mh = 0; mh < J.m_halves; ++mh) {
         const int m = mh * 128 + r;
 #pragma unroll 1
         for (int c0 = 0; c0 < N_TILE; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * N_TILE + c0, v);
           tmem_ld_wait();
-          if (m < p.m_valid) {
-            float* o = p.dW + (size_t)m * p.ld_w + n0 + c0;
+          if (m < J.m_valid) {
+            float* o = J.dW + (size_t)m * J.ld_w + J.n0 + c0;
 #pragma unroll
             for (int e = 0; e < 32; ++e)
-              if (n0 + c0 + e < p.n_valid) atomicAdd(o + e, __uint_as_float(v[e]));
+              if (J.n0 + c0 + e < J.n_valid) atomicAdd(o + e, __uint_as_float(v[e]));
           }
         }
       }
