@@ -150,6 +150,7 @@ class Graph(torch.nn.Module):
         self._grad_slices = None
         self._local = None
         self._norms = (0.0, 0.0)
+        self.data_parallel = None        # None: follow torch.distributed; False: force single-rank behaviour
 
     # ------------------------------------------------------------------ engine plumbing
     def _mask_mode(self):
@@ -166,6 +167,9 @@ class Graph(torch.nn.Module):
             ps += [l.weight for l in lins] + [l.bias for l in lins]
         return ps
 
+    def _dp(self):
+        return _dist_on() if self.data_parallel is None else bool(self.data_parallel)
+
     def _ensure_engine(self):
         if self.engine is not None:
             return
@@ -173,8 +177,8 @@ class Graph(torch.nn.Module):
         dev = self.warp_param.weight.device
         if dev.type != "cuda":
             raise RuntimeError("Graph must live on a CUDA device (marf_b200 has no CPU path)")
-        rank = dist.get_rank() if _dist_on() else 0
-        world = dist.get_world_size() if _dist_on() else 1
+        rank = dist.get_rank() if self._dp() else 0
+        world = dist.get_world_size() if self._dp() else 1
         self.engine = PlanarEngine(
             H=opt.H, W=opt.W, patch_H=opt.patch_H, patch_W=opt.patch_W, batch_size=opt.batch_size,
             layers=list(opt.arch.layers[1:]), skip=list(opt.arch.skip or []),
@@ -215,7 +219,7 @@ class Graph(torch.nn.Module):
                     masks_eroded=cut(images.get("masks_eroded"), torch.float32), edges=cut(images.get("edges"), torch.float64))
         # global loss normalisers that do not depend on the forward pass
         n_rgb = n_edge = 0.0
-        if _dist_on() and not self.opt.use_implicit_mask:
+        if self._dp() and not self.opt.use_implicit_mask:
             if self.opt.use_masks:
                 s = torch.stack([loc.masks.double().sum(),
                                  loc.masks_eroded.double().sum() if loc.masks_eroded is not None else torch.zeros((), dtype=torch.float64, device=e.device)])
@@ -267,7 +271,7 @@ class Graph(torch.nn.Module):
                       g_mask_w=gv[2 * nl + 1:2 * nl + 1 + nm], g_mask_b=gv[2 * nl + 1 + nm:2 * nl + 1 + 2 * nm])
         c_rgb, c_mask, c_edge, _ = self.loss_coefficients()
         kw["coef"] = (c_rgb, c_mask, c_edge)
-        if not _dist_on():
+        if not self._dp():
             sums = e.step(**kw)
         elif not implicit:
             kw["norm_rgb"], kw["norm_edge"] = self._norms

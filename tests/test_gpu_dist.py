@@ -1,0 +1,22 @@
+"""GPU, needs >= 2 devices: launches tests/dist_worker.py under torchrun (N-rank result == 1-rank result)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_two_ranks_match_one_rank(precision):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(ROOT, "tests", "dist_worker.py"), "--precision", precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0 and "all cases OK" in r.stdout
