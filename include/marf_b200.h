@@ -171,6 +171,25 @@ int marf_warp_points(marf_handle* h, const float* xy, const float* warp, int32_t
 int marf_compute_edges(marf_handle* h, const float* images, int32_t n, int32_t c, int32_t rows, int32_t w,
                        double* out, void* stream);
 
+/* Device-side Adam over a list of tensors in one launch (torch.optim.Adam defaults: no weight decay, no amsgrad;
+ * model/planar.py:98-99,197), plus the `warp.fix_first` reset of the loop tail (model/planar.py:157-158):
+ * after the update the first `zero_count` elements of tensor `zero_tensor` are set to 0 (moments keep evolving,
+ * as in the reference).  `step` is the 1-based step count used for the bias corrections. */
+typedef struct marf_adam_io {
+  int32_t n_tensors;
+  float* const* params;       /* host array of device ptrs */
+  const float* const* grads;
+  float* const* exp_avg;
+  float* const* exp_avg_sq;
+  const int64_t* numel;       /* host array */
+  const float* lr;            /* host array, per tensor */
+  float beta1, beta2, eps;
+  int64_t step;
+  int32_t zero_tensor;        /* -1: none */
+  int32_t zero_count;
+} marf_adam_io;
+int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream);
+
 /* diagnostic: run ONE tensor-core kernel (tcgen05) on fp32 device arrays that are rounded to bf16 inside.
  * mode 0: relu(A[rows,K] W[N,K]^T + aux[N]); 1: (A W^T)*(aux[rows,N]>0); 2: plain fp32 out, N=64;
  * 3: out[N,K] = A[rows,N]^T aux[rows,K] (the dW kernel).  Synchronises `stream`.  Used by tests/ only. */

@@ -633,6 +633,48 @@ extern "C" int marf_warp_corners(marf_handle* h, const float* warp, int32_t n, f
   return MARF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ fused Adam
+struct AdamEntry { float* p; const float* g; float* m; float* v; long long n; float lr; int zero_n; };
+constexpr int kMaxAdam = 40;
+struct AdamTable { AdamEntry e[kMaxAdam]; float beta1, beta2, eps, bc1, bc2_sqrt; };
+
+__global__ void k_adam(const __grid_constant__ AdamTable t) {
+  const AdamEntry& E = t.e[blockIdx.y];
+  const float step_size = E.lr / t.bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < E.n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = E.g[i];
+    float m = E.m[i], v = E.v[i];
+    m = m + (g - m) * (1.0f - t.beta1);                       // exp_avg.lerp_(grad, 1-beta1)
+    v = v * t.beta2 + g * g * (1.0f - t.beta2);               // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+    const float denom = sqrtf(v) / t.bc2_sqrt + t.eps;
+    float p = E.p[i] - step_size * (m / denom);
+    if (i < E.zero_n) p = 0.0f;                               // warp.fix_first
+    E.m[i] = m; E.v[i] = v; E.p[i] = p;
+  }
+}
+
+extern "C" int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream) {
+  if (!h) return MARF_ERR_INVALID;
+  if (!io || io->n_tensors <= 0 || io->n_tensors > kMaxAdam || !io->params || !io->grads || !io->exp_avg || !io->exp_avg_sq ||
+      !io->numel || !io->lr || io->step < 1)
+    return fail(h, MARF_ERR_INVALID, "bad adam io");
+  AdamTable t;
+  long long max_n = 0;
+  for (int i = 0; i < io->n_tensors; ++i) {
+    t.e[i].p = io->params[i]; t.e[i].g = io->grads[i]; t.e[i].m = io->exp_avg[i]; t.e[i].v = io->exp_avg_sq[i];
+    t.e[i].n = io->numel[i]; t.e[i].lr = io->lr[i];
+    t.e[i].zero_n = (i == io->zero_tensor) ? io->zero_count : 0;
+    max_n = std::max<long long>(max_n, io->numel[i]);
+  }
+  t.beta1 = io->beta1; t.beta2 = io->beta2; t.eps = io->eps;
+  t.bc1 = (float)(1.0 - pow((double)io->beta1, (double)io->step));
+  t.bc2_sqrt = (float)sqrt(1.0 - pow((double)io->beta2, (double)io->step));
+  dim3 grid((unsigned)std::min<long long>((max_n + 255) / 256, 64), io->n_tensors);
+  k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(t);
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
+
 __global__ void k_warp_points(const float* __restrict__ xy, const float* __restrict__ Hm, int n, int p,
                               float* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -25,10 +25,11 @@ using bf16 = __nv_bfloat16;
   } while (0)
 
 // ------------------------------------------------------------------------------------------------ SIMT helpers
+template <int LT>   // LT > 0: compile-time band count (registers); LT == 0: runtime g.L (local array)
 __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, bf16* __restrict__ X0, int ld) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
-  uint32_t* o = reinterpret_cast<uint32_t*>(X0 + (size_t)t * ld);
+  uint4* o = reinterpret_cast<uint4*>(X0 + (size_t)t * ld);
   float f[64];
 #pragma unroll
   for (int j = 0; j < 64; ++j) f[j] = 0.f;
@@ -39,20 +40,23 @@ __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, b
     grid_xy(g, r, c, x, y);
     apply_h(Hm + 9 * (b + g.patch_offset), x, y, u, v, qz);
     f[0] = u; f[1] = v;
-    const int L = g.L;
+    const int L = LT > 0 ? LT : g.L;
 #pragma unroll
-    for (int k = 0; k < kMaxBands; ++k) {
-      if (k < L) {
+    for (int k = 0; k < (LT > 0 ? LT : kMaxBands); ++k) {
+      if (k < L && 2 + 3 * L + k < 64) {
         float su, cu, sv, cv;
         sincosf(u * g.band_f[k], &su, &cu);
         sincosf(v * g.band_f[k], &sv, &cv);
         float wk = g.band_w[k];
-        // 2+4L <= 64 for L <= 15
-        if (2 + 3 * L + k < 64) { f[2 + k] = su * wk; f[2 + L + k] = cu * wk; f[2 + 2 * L + k] = sv * wk; f[2 + 3 * L + k] = cv * wk; }
+        f[2 + k] = su * wk; f[2 + L + k] = cu * wk; f[2 + 2 * L + k] = sv * wk; f[2 + 3 * L + k] = cv * wk;
       }
     }
   }
-  for (int j = 0; j < ld / 2; ++j) o[j] = j < 32 ? tc::pack_bf16(f[2 * j], f[2 * j + 1]) : 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                      tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+  for (int j = 8; j < ld / 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // mask-head features (model/planar.py:342-349) in bf16, one block per pixel row
@@ -120,35 +124,51 @@ __global__ void k_thin_fwd(int n, const bf16* __restrict__ X, int ld, const floa
   for (int o = 0; o < OUT; ++o) bo[o] = bias[o];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  for (int row = warp; row < n; row += nwarps) {
-    float acc[OUT];
+  constexpr int R = 4;                               // rows in flight per warp
+  for (int row0 = warp * R; row0 < n; row0 += nwarps * R) {
+    uint4 raw[R][KCH];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) acc[o] = 0.f;
+    for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int c = 0; c < KCH; ++c) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + c * 256 + lane * 8);
-      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+      for (int c = 0; c < KCH; ++c)
+        raw[i][c] = row0 + i < n ? *reinterpret_cast<const uint4*>(X + (size_t)(row0 + i) * ld + c * 256 + lane * 8)
+                                 : make_uint4(0u, 0u, 0u, 0u);
+    float acc[R][OUT];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+    for (int i = 0; i < R; ++i) {
 #pragma unroll
-        for (int o = 0; o < OUT; ++o) acc[o] = fmaf(xv, w[c][o][e], acc[o]);
+      for (int o = 0; o < OUT; ++o) acc[i][o] = 0.f;
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) {
+        const uint32_t w4[4] = {raw[i][c].x, raw[i][c].y, raw[i][c].z, raw[i][c].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+#pragma unroll
+          for (int o = 0; o < OUT; ++o) acc[i][o] = fmaf(xv, w[c][o][e], acc[i][o]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) acc[o] = warp_sum(acc[o]);
-    if (lane == 0) {
-      float4 r4 = make_float4(acc[0] + bo[0], OUT > 1 ? acc[OUT > 1 ? 1 : 0] + bo[OUT > 1 ? 1 : 0] : 0.f,
-                              OUT > 2 ? acc[OUT > 2 ? 2 : 0] + bo[OUT > 2 ? 2 : 0] : 0.f, 0.f);
-      *reinterpret_cast<float4*>(out + (size_t)row * 4) = r4;
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int o = 0; o < OUT; ++o) acc[i][o] = warp_sum(acc[i][o]);
+    if (lane < R && row0 + lane < n) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (lane == i) { a0 = acc[i][0]; a1 = OUT > 1 ? acc[i][OUT > 1 ? 1 : 0] : 0.f; a2 = OUT > 2 ? acc[i][OUT > 2 ? 2 : 0] : 0.f; }
+      *reinterpret_cast<float4*>(out + (size_t)(row0 + lane) * 4) =
+          make_float4(a0 + bo[0], OUT > 1 ? a1 + bo[OUT > 1 ? 1 : 0] : 0.f, OUT > 2 ? a2 + bo[OUT > 2 ? 2 : 0] : 0.f, 0.f);
     }
   }
 }
 
-// dY_prev[row,k] = (sum_o dl[row,o] W[o,k]) * (X[row,k] > 0)     (bf16 out); thread owns a fixed k-octet
+// dY_prev[row,k] = (sum_o dl[row,o] W[o,k]) * relu_mask[row,k]     (bf16 out); thread owns a fixed k-octet;
+// the mask is the 1-bit-per-activation map the forward epilogue wrote
 template <int OUT>
 __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const float* __restrict__ W,
-                          const bf16* __restrict__ X, int ld, bf16* __restrict__ dY, int ldy) {
+                          const uint32_t* __restrict__ bits, int bits_ld, bf16* __restrict__ dY, int ldy) {
   const int per_row = width / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int total_threads = gridDim.x * blockDim.x;         // multiple of per_row (host guarantees)
@@ -161,20 +181,29 @@ __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const 
   for (int row = tid / per_row; row < n; row += total_threads / per_row) {
     const float4 d4 = *reinterpret_cast<const float4*>(dl + (size_t)row * 4);
     const float d[3] = {d4.x, d4.y, d4.z};
-    const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + k);
-    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+    const uint32_t mb = (bits[(size_t)row * bits_ld + (k >> 5)] >> (k & 31)) & 0xFFu;
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const uint32_t hbits = (w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
       float s = 0.f;
 #pragma unroll
       for (int o = 0; o < OUT; ++o) s = fmaf(d[o], w[o][e], s);
-      f[e] = ((hbits & 0x8000u) == 0 && (hbits & 0x7FFFu) != 0) ? s : 0.f;
+      f[e] = ((mb >> e) & 1u) ? s : 0.f;
     }
     *reinterpret_cast<uint4*>(dY + (size_t)row * ldy + k) =
         make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
   }
+}
+
+// bit c of row = (X[row,c] > 0)   (diagnostics: builds the mask the forward epilogue would have written)
+static __global__ void k_make_bits(int rows, int width, const float* __restrict__ X, uint32_t* __restrict__ bits) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int words = width / 32;
+  if (i >= rows * words) return;
+  int r = i / words, wd = i - r * words;
+  uint32_t m = 0;
+  for (int e = 0; e < 32; ++e) m |= (X[(size_t)r * width + wd * 32 + e] > 0.f ? 1u : 0u) << e;
+  bits[i] = m;
 }
 
 // dW[o,k] += sum_row dl[row,o] X[row,k] ; db[o] += sum_row dl[row,o]   (block = (width/8, 8); smem reduce over y;
@@ -191,19 +220,29 @@ __global__ void k_thin_dw(int n, int width, const float* __restrict__ dl, const 
   for (int o = 0; o < OUT; ++o) { bacc[o] = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[o][e] = 0.f; }
-#pragma unroll 2
-  for (int row = r0 + threadIdx.y; row < r1; row += blockDim.y) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(X + (size_t)row * ld + kq);
-    const float4 d4 = *reinterpret_cast<const float4*>(dl + (size_t)row * 4);
-    const float d[3] = {d4.x, d4.y, d4.z};
-    const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+  constexpr int R = 4;
+  for (int rowb = r0 + threadIdx.y; rowb < r1; rowb += blockDim.y * R) {
+    uint4 raw[R];
+    float4 d4[R];
 #pragma unroll
-    for (int o = 0; o < OUT; ++o) bacc[o] += d[o];
+    for (int i = 0; i < R; ++i) {
+      const int row = rowb + i * blockDim.y;
+      const bool ok = row < r1;
+      raw[i] = ok ? *reinterpret_cast<const uint4*>(X + (size_t)row * ld + kq) : make_uint4(0u, 0u, 0u, 0u);
+      d4[i] = ok ? *reinterpret_cast<const float4*>(dl + (size_t)row * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+    for (int i = 0; i < R; ++i) {
+      const float d[3] = {d4[i].x, d4[i].y, d4[i].z};
+      const uint32_t w4[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
 #pragma unroll
-      for (int o = 0; o < OUT; ++o) acc[o][e] = fmaf(d[o], xv, acc[o][e]);
+      for (int o = 0; o < OUT; ++o) bacc[o] += d[o];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xv = __uint_as_float(((w4[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu) << 16);
+#pragma unroll
+        for (int o = 0; o < OUT; ++o) acc[o][e] = fmaf(d[o], xv, acc[o][e]);
+      }
     }
   }
   const int stride = OUT * width + OUT;
@@ -276,6 +315,7 @@ struct BfChain {
   int ld[MARF_MAX_LAYERS + 1] = {};
   CUtensorMap tmAct128[MARF_MAX_LAYERS + 1];   // box {64,128}: GEMM A loads / epilogue stores / mask loads
   CUtensorMap tmAct64[MARF_MAX_LAYERS + 1];    // box {64,64}: dW loads
+  uint32_t* bits[MARF_MAX_LAYERS + 1] = {};  // bits[l]: 1-bit ReLU mask of act[l] (l >= 1), [chunk, ld[l]/32] words
   bf16* dY[MARF_MAX_LAYERS] = {};         // dY[l]: gradient wrt the output of layer l [chunk, np(l)] (kept for the dW pass)
   CUtensorMap tmDY128[MARF_MAX_LAYERS], tmDY64[MARF_MAX_LAYERS];
   float* logits = nullptr;                // [chunk,4] fp32
@@ -343,6 +383,10 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     if (rc) return rc;
     rc = make_tmap(h, S, &B.tmAct64[l], B.act[l], h->chunk, B.ld[l], 64);
     if (rc) return rc;
+    if (l >= 1) {
+      B.bits[l] = (uint32_t*)ws_alloc(h, (size_t)h->chunk * (B.ld[l] / 32) * 4);
+      if (!B.bits[l]) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (mask bits)");
+    }
     if (l < F.n - 1) {
       B.dY[l] = (bf16*)ws_alloc(h, (size_t)h->chunk * B.L[l].np * 2);
       if (!B.dY[l]) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (dY)");
@@ -414,6 +458,8 @@ static int launch_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int l, int ro
   p.n_tiles = rows / 128;
   p.k_chunks = L.kp / 64;
   p.bias = B.f32->bp[l];
+  p.bits_out = B.bits[l + 1];
+  p.bits_ld = B.ld[l + 1] / 32;
   int n_tile = (L.kp > 256 && L.np > 128) ? 128 : std::min(L.np, 256);
   dim3 grid(std::min(p.n_tiles, std::max(1, S->num_sms / (L.np / n_tile))), L.np / n_tile);
   int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
@@ -432,6 +478,8 @@ static int launch_dx(marf_handle* h, cudaStream_t st, BfChain& B, int l, int row
   tc::GemmParams p{};
   p.n_tiles = rows / 128;
   p.k_chunks = L.np / 64;                    // contraction over the layer's outputs
+  p.bits_in = B.bits[l];
+  p.bits_ld = B.ld[l] / 32;
   int n_total = L.kp;                        // produces the layer's (padded) inputs = np of layer l-1
   int n_tile = std::min(n_total, 256);
   if (n_total % n_tile) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: input width must tile by 256/128/64");
@@ -516,7 +564,7 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 static int thin_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* W, const float* bias) {
   int l = B.n - 1;
   int width = B.L[l].k_in, out = B.L[l].k_out;
-  int blocks = std::min((rows + 7) / 8, h->bf16->num_sms * 8);
+  int blocks = std::min((rows + 31) / 32, h->bf16->num_sms * 8);
   if (out == 3 && width == 256) k_thin_fwd<3, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
   else if (out == 3 && width == 512) k_thin_fwd<3, 2><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
   else if (out == 1 && width == 256) k_thin_fwd<1, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
@@ -542,11 +590,11 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   if (out == 3) {
     k_thin_dw<3><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<3><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], B.dY[l - 1], B.L[l - 1].np);
+    k_thin_dx<3><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   } else {
     k_thin_dw<1><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<1><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.act[l], B.ld[l], B.dY[l - 1], B.L[l - 1].np);
+    k_thin_dx<1><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   }
   BF_LAUNCH(h);
   return MARF_OK;
@@ -645,7 +693,13 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
   const marf_config& c = h->cfg;
   PxRange rg = bf_chunk(h, ci);
   bool implicit = c.mask_mode == MARF_MASK_IMPLICIT;
-  k_encode_bf16<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+  {
+    dim3 eg((rg.padded + 127) / 128);
+    if (h->geo.L == 8) k_encode_bf16<8><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else if (h->geo.L == 10) k_encode_bf16<10><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else if (h->geo.L == 4) k_encode_bf16<4><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else k_encode_bf16<0><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+  }
   BF_LAUNCH(h);
   int rc = bf_chain_forward(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1], io->mlp_b[c.n_layers - 1]);
   if (rc) return rc;
@@ -821,14 +875,18 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
           else rc = MARF_ERR_INVALID;
         }
       } else {
-        dAux = to_bf(aux, rows, N);
-        if (!dAux) return MARF_ERR_CUDA;
-        if (!rc) rc = make_tmap(&tmp, &S, &tM, dAux, rows, N, 128);
+        uint32_t* dBits = nullptr;
+        if (cudaMalloc(&dBits, (size_t)rows * (N / 32) * 4) != cudaSuccess) return MARF_ERR_CUDA;
+        k_make_bits<<<(rows * (N / 32) + 255) / 256, 256, 0, st>>>(rows, N, aux, dBits);
+        p.bits_in = dBits;
+        p.bits_ld = N / 32;
         if (!rc) {
-          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tM, p);
-          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tM, p);
+          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
+          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
           else rc = MARF_ERR_INVALID;
         }
+        cudaStreamSynchronize(st);
+        cudaFree(dBits);
       }
       if (!rc) {
         long long tot = (long long)rows * N;

@@ -30,6 +30,9 @@ struct GemmParams {
   float* out_f32;       // EPI_PLAIN_F32: [rows, ld_out] fp32, first n_store columns written
   int ld_out;
   int n_store;
+  uint32_t* bits_out;   // EPI_BIAS_RELU: optional [rows, bits_ld] words, bit c of a row = (output column c > 0)
+  const uint32_t* bits_in;  // EPI_RELU_MASK: the ReLU mask of the layer input, same layout
+  int bits_ld;          // words per row (= padded width / 32)
 };
 
 struct GemmSmem {       // offsets computed on host and device identically
@@ -81,7 +84,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmW);
     if (kStaged) prefetch_tmap(&tmOut);
-    if (EPI == EPI_RELU_MASK) prefetch_tmap(&tmMask);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); mbar_init(&mask_full[a], 1); }
@@ -141,31 +143,21 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool leader = threadIdx.x == 64;
     const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
     uint32_t g = 0, t_iter = 0;
-    if (EPI == EPI_RELU_MASK && leader && (int)blockIdx.x < p.n_tiles) {
-      mbar_expect_tx(&mask_full[0], kChunkBytes);
-      tma_load_2d(sOut, &tmMask, n0, blockIdx.x * kTileM, &mask_full[0]);
-    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_iter) {
       const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
+      uint32_t mbits[2 * kSlabs];
+      if (EPI == EPI_RELU_MASK) {
+        const uint32_t* bp = p.bits_in + (size_t)(tile * kTileM + r) * p.bits_ld + n0 / 32;
+#pragma unroll
+        for (int i = 0; i < 2 * kSlabs; ++i) mbits[i] = bp[i];
+      }
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int j = 0; j < kSlabs; ++j, ++g) {
         const uint32_t b = g & 1;
         uint8_t* ob = sOut + b * kChunkBytes;
-        if (EPI == EPI_RELU_MASK) {
-          if (leader) {
-            // the other buffer is free once the store issued for the previous slab has finished reading it
-            bulk_wait_read<0>();
-            int nt = tile, nj = j + 1;
-            if (nj == kSlabs) { nj = 0; nt = tile + gridDim.x; }
-            if (nt < p.n_tiles) {
-              mbar_expect_tx(&mask_full[b ^ 1], kChunkBytes);
-              tma_load_2d(sOut + (b ^ 1) * kChunkBytes, &tmMask, n0 + nj * 64, nt * kTileM, &mask_full[b ^ 1]);
-            }
-          }
-          mbar_wait(&mask_full[b], (g >> 1) & 1);
-        } else if (EPI == EPI_BIAS_RELU) {
+        if (kStaged) {
           if (leader) bulk_wait_read<1>();             // the store issued two slabs ago (same buffer) is done reading
           named_bar_sync(1, 128);
         }
@@ -185,6 +177,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (n0 + j * 64 + c4 * 4 < p.n_store)
               *reinterpret_cast<uint4*>(o + c4 * 4) = make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
         } else {
+          uint32_t obits[2] = {0u, 0u};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             uint8_t* addr = ob + sw_row + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4);
@@ -193,20 +186,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i * 8 + e]);
             if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e] + sBias[j * 64 + i * 8 + e], 0.f);
-            } else {
-              const uint4 m = *reinterpret_cast<const uint4*>(addr);
-              const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
-#pragma unroll
               for (int e = 0; e < 8; ++e) {
-                // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                const uint32_t h = (mw[e >> 1] >> ((e & 1) * 16)) & 0xFFFFu;
-                f[e] = ((h & 0x8000u) == 0 && (h & 0x7FFFu) != 0) ? f[e] : 0.f;
+                f[e] = fmaxf(f[e] + sBias[j * 64 + i * 8 + e], 0.f);
+                if (f[e] > 0.f) obits[i >> 2] |= 1u << ((i & 3) * 8 + e);
               }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = ((mbits[2 * j + (i >> 2)] >> ((i & 3) * 8 + e)) & 1u) ? f[e] : 0.f;
             }
             *reinterpret_cast<uint4*>(addr) =
                 make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
           }
+          if (EPI == EPI_BIAS_RELU && p.bits_out)
+            *reinterpret_cast<uint2*>(p.bits_out + (size_t)(tile * kTileM + r) * p.bits_ld + (n0 + j * 64) / 32) =
+                make_uint2(obits[0], obits[1]);
           fence_proxy_async_smem();
           named_bar_sync(2, 128);
           if (leader) {

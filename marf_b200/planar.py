@@ -376,6 +376,17 @@ class Model(torch.nn.Module):
         if opt.optim.sched:
             kwargs = {k: v for k, v in opt.optim.sched.items() if k != "type"}
             self.sched = getattr(torch.optim.lr_scheduler, opt.optim.sched.type)(self.optim, **kwargs)
+        if opt.get("fused_optimizer"):
+            if opt.optim.algo != "Adam" or opt.optim.sched:
+                raise NotImplementedError("fused_optimizer implements optim.algo=Adam without a scheduler")
+            from .optim import FusedAdam
+            g = self.graph
+            g._ensure_engine()
+            ps = g.step_params()
+            n_img = 2 * len(g.neural_image.mlp)
+            lrs = [opt.optim.lr] * n_img + [opt.optim.lr_warp] + [opt.optim.lr_mask] * (len(ps) - n_img - 1)
+            self.fused_tail = FusedAdam(g.engine, [p.data for p in ps], g._grad_views, lrs, zero_tensor=n_img,
+                                        zero_count=opt.warp.dof if opt.warp.fix_first else 0)
 
     def setup_visualizer(self):
         print("setting up visualizers...")
@@ -431,12 +442,19 @@ class Model(torch.nn.Module):
     def train_iteration(self, var, loader):
         """model/planar.py:187-209."""
         self.timer.it_start = time.time()
-        self.optim.zero_grad()
-        var = self.graph.forward(var, mode="train")
-        loss = self.graph.compute_loss(var, mode="train")
-        loss = self.summarize_loss(loss)
-        loss.all.backward()
-        self.optim.step()
+        if self.fused_tail is not None:
+            # device-side tail (SURVEY.md §8 f1): the step already produced d(loss.all)/dθ; one Adam launch follows
+            with torch.no_grad():
+                var = self.graph.forward(var, mode="train")
+                loss = self.summarize_loss(self.graph.compute_loss(var, mode="train"))
+            self.fused_tail.step()
+        else:
+            self.optim.zero_grad()
+            var = self.graph.forward(var, mode="train")
+            loss = self.graph.compute_loss(var, mode="train")
+            loss = self.summarize_loss(loss)
+            loss.all.backward()
+            self.optim.step()
         if self.sched:
             pass  # the reference constructs the scheduler but never steps it (model/planar.py:101-104)
         if (self.it + 1) % self.opt.freq.scalar == 0:

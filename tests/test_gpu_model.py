@@ -33,6 +33,8 @@ class _Loader:
 @pytest.mark.parametrize("name,over", [
     ("train_small_c2f", dict(barf_c2f=[0.0, 0.4], use_edges=False)),
     ("train_small_edges", dict(barf_c2f=None, use_edges=True)),
+    ("train_small_c2f", dict(barf_c2f=[0.0, 0.4], use_edges=False, fused_optimizer=True)),
+    ("train_small_edges", dict(barf_c2f=None, use_edges=True, fused_optimizer=True)),
 ])
 def test_train_iteration_matches_reference_trajectory(tmp_path, name, over):
     from marf_b200.attrdict import AttrDict
