@@ -181,14 +181,15 @@ __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const 
   for (int row = tid / per_row; row < n; row += total_threads / per_row) {
     const float4 d4 = *reinterpret_cast<const float4*>(dl + (size_t)row * 4);
     const float d[3] = {d4.x, d4.y, d4.z};
-    const uint32_t mb = (bits[(size_t)row * bits_ld + (k >> 5)] >> (k & 31)) & 0xFFu;
+    // layout: bit t <- column 2t, bit 16+t <- column 2t+1 inside each 32-column group
+    const uint32_t mw = bits[(size_t)row * bits_ld + (k >> 5)] >> ((k & 31) >> 1);
     float f[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       float s = 0.f;
 #pragma unroll
       for (int o = 0; o < OUT; ++o) s = fmaf(d[o], w[o][e], s);
-      f[e] = ((mb >> e) & 1u) ? s : 0.f;
+      f[e] = ((mw >> ((e >> 1) + 16 * (e & 1))) & 1u) ? s : 0.f;
     }
     *reinterpret_cast<uint4*>(dY + (size_t)row * ldy + k) =
         make_uint4(tc::pack_bf16(f[0], f[1]), tc::pack_bf16(f[2], f[3]), tc::pack_bf16(f[4], f[5]), tc::pack_bf16(f[6], f[7]));
@@ -202,7 +203,7 @@ static __global__ void k_make_bits(int rows, int width, const float* __restrict_
   if (i >= rows * words) return;
   int r = i / words, wd = i - r * words;
   uint32_t m = 0;
-  for (int e = 0; e < 32; ++e) m |= (X[(size_t)r * width + wd * 32 + e] > 0.f ? 1u : 0u) << e;
+  for (int e = 0; e < 32; ++e) m |= (X[(size_t)r * width + wd * 32 + e] > 0.f ? 1u : 0u) << ((e >> 1) + 16 * (e & 1));
   bits[i] = m;
 }
 
@@ -460,6 +461,9 @@ static int launch_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int l, int ro
   p.bias = B.f32->bp[l];
   p.bits_out = B.bits[l + 1];
   p.bits_ld = B.ld[l + 1] / 32;
+  p.reverse = l & 1;                         // alternate direction: start where the previous layer just finished
+  p.load_policy = tc::kEvictFirst;           // inputs are not read again before the backward pass
+  p.store_policy = tc::kEvictLast;           // outputs are the next launch's inputs
   int n_tile = (L.kp > 256 && L.np > 128) ? 128 : std::min(L.np, 256);
   dim3 grid(std::min(p.n_tiles, std::max(1, S->num_sms / (L.np / n_tile))), L.np / n_tile);
   int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
@@ -480,6 +484,9 @@ static int launch_dx(marf_handle* h, cudaStream_t st, BfChain& B, int l, int row
   p.k_chunks = L.np / 64;                    // contraction over the layer's outputs
   p.bits_in = B.bits[l];
   p.bits_ld = B.ld[l] / 32;
+  p.reverse = l & 1;
+  p.load_policy = tc::kEvictFirst;
+  p.store_policy = tc::kEvictLast;
   int n_total = L.kp;                        // produces the layer's (padded) inputs = np of layer l-1
   int n_tile = std::min(n_total, 256);
   if (n_total % n_tile) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: input width must tile by 256/128/64");
@@ -505,6 +512,9 @@ static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain& B, int rows) {
   p.out_f32 = S->dX0;
   p.ld_out = 64;
   p.n_store = pad4(L.k_in);
+  p.reverse = 0;
+  p.load_policy = tc::kEvictFirst;
+  p.store_policy = tc::kEvictNormal;
   dim3 grid(std::min(p.n_tiles, S->num_sms), 1);
   int smem = tc::gemm_smem(64, p.k_chunks, false).total + 1024;
   tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[0], L.tmWt, B.tmDY128[0], B.tmDY128[0], p);
@@ -554,8 +564,8 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     for (int i = 0; i < nj; ++i) jobs.j[i].rows_per_cta = per;
     dim3 grid(ctas, nj);
     int smem = tc::kDwStages * max_stage + 256 + 1024;
-    if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(jobs);
-    else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(jobs);
+    if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kDwThreads, smem, st>>>(jobs);
+    else tc::k_tc_dw<64><<<grid, tc::kDwThreads, smem, st>>>(jobs);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -858,6 +868,9 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     tc::GemmParams p{};
     p.n_tiles = rows / 128;
     p.k_chunks = K / 64;
+    p.reverse = (rows / 128) & 1;
+    p.load_policy = tc::kEvictFirst;
+    p.store_policy = tc::kEvictLast;
     dim3 grid(std::min(p.n_tiles, std::max(1, 148 / (N / n_tile))), N / n_tile);
     if (mode == 2) {
       p.out_f32 = out; p.ld_out = 64; p.n_store = 64;
@@ -918,8 +931,8 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     int smem = tc::kDwStages * stage + 256 + 1024;
     dim3 grid(ctas, n_tiles_n);
     if (!rc) {
-      if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kThreads, smem, st>>>(jobs);
-      else tc::k_tc_dw<64><<<grid, tc::kThreads, smem, st>>>(jobs);
+      if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kDwThreads, smem, st>>>(jobs);
+      else tc::k_tc_dw<64><<<grid, tc::kDwThreads, smem, st>>>(jobs);
     }
   } else {
     return MARF_ERR_INVALID;

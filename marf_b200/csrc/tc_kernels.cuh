@@ -19,7 +19,8 @@ constexpr int kTileM = 128;          // pixel rows per tile (= TMEM lanes)
 constexpr int kChunkK = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int kChunkBytes = kTileM * 128;   // one [128 x 64] bf16 operand chunk
 constexpr int kStages = 4;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;         // k_tc_gemm: producer warp, MMA warp, 8 epilogue warps
+constexpr int kDwThreads = 192;       // k_tc_dw: producer warp, MMA warp, 4 epilogue warps
 
 enum { EPI_BIAS_RELU = 0, EPI_RELU_MASK = 1, EPI_PLAIN_F32 = 2 };
 
@@ -33,6 +34,9 @@ struct GemmParams {
   uint32_t* bits_out;   // EPI_BIAS_RELU: optional [rows, bits_ld] words, bit c of a row = (output column c > 0)
   const uint32_t* bits_in;  // EPI_RELU_MASK: the ReLU mask of the layer input, same layout
   int bits_ld;          // words per row (= padded width / 32)
+  int reverse;          // walk the tiles last-to-first (the previous layer's newest output is still in L2)
+  unsigned long long load_policy;   // L2 cache hint of the streamed A tiles
+  unsigned long long store_policy;  // L2 cache hint of the output tiles
 };
 
 struct GemmSmem {       // offsets computed on host and device identically
@@ -86,12 +90,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (kStaged) prefetch_tmap(&tmOut);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); mbar_init(&mask_full[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); mbar_init(&mask_full[a], 1); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   if (EPI == EPI_BIAS_RELU && warp >= 2)
-    for (int i = threadIdx.x - 64; i < N_TILE; i += 128) sBias[i] = p.bias[n0 + i];
+    for (int i = threadIdx.x - 64; i < N_TILE; i += 256) sBias[i] = p.bias[n0 + i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -103,13 +107,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
       for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &tmW, c * kChunkK, n0, w_full);
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+      for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x) {
+        const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
         for (int c = 0; c < p.k_chunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], kChunkBytes);
-          tma_load_2d(sA + s * kChunkBytes, &tmA, c * kChunkK, tile * kTileM, &full[s]);
+          tma_load_2d_hint(sA + s * kChunkBytes, &tmA, c * kChunkK, tile * kTileM, &full[s], p.load_policy);
         }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -137,13 +143,17 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (128 threads)
-    const int q = warp & 3;
+    // ------------------------------------------------------------------ epilogue: 2 groups x 4 warps (256 threads)
+    // group g handles the 64-column slabs g, g+2, ...; each group owns one staging buffer and two named barriers.
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int grp = (warp - 2) >> 2;
     const int r = q * 32 + lane;                       // tile row == TMEM lane
-    const bool leader = threadIdx.x == 64;
+    const bool gleader = threadIdx.x == 64 + 128 * grp;
     const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
-    uint32_t g = 0, t_iter = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_iter) {
+    uint8_t* ob = sOut + grp * kChunkBytes;
+    uint32_t t_iter = 0;
+    for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x, ++t_iter) {
+      const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
       const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
       uint32_t mbits[2 * kSlabs];
       if (EPI == EPI_RELU_MASK) {
@@ -154,13 +164,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
 #pragma unroll
-      for (int j = 0; j < kSlabs; ++j, ++g) {
-        const uint32_t b = g & 1;
-        uint8_t* ob = sOut + b * kChunkBytes;
-        if (kStaged) {
-          if (leader) bulk_wait_read<1>();             // the store issued two slabs ago (same buffer) is done reading
-          named_bar_sync(1, 128);
-        }
+      for (int j = 0; j < kSlabs; ++j) {
+        if ((j & 1) != grp) continue;
         uint32_t v[64];
         {
           uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -168,8 +173,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + a * N_TILE + j * 64;
           tmem_ld32(taddr, v0);
           tmem_ld32(taddr + 32, v1);
-          tmem_ld_wait();
         }
+        if (kStaged) {
+          if (gleader) bulk_wait_read<0>();            // this group's previous store has finished reading the buffer
+          named_bar_sync(1 + 2 * grp, 128);
+        }
+        tmem_ld_wait();
         if (EPI == EPI_PLAIN_F32) {
           float* o = p.out_f32 + (size_t)(tile * kTileM + r) * p.ld_out + n0 + j * 64;
 #pragma unroll
@@ -177,33 +186,38 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if (n0 + j * 64 + c4 * 4 < p.n_store)
               *reinterpret_cast<uint4*>(o + c4 * 4) = make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
         } else {
+          // mask-bit layout inside a 32-column group: bit t <- column 2t, bit 16+t <- column 2t+1 (t = 0..15)
           uint32_t obits[2] = {0u, 0u};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint8_t* addr = ob + sw_row + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4);
-            float f[8];
+            uint32_t w[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i * 8 + e]);
-            if (EPI == EPI_BIAS_RELU) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                f[e] = fmaxf(f[e] + sBias[j * 64 + i * 8 + e], 0.f);
-                if (f[e] > 0.f) obits[i >> 2] |= 1u << ((i & 3) * 8 + e);
+            for (int pr = 0; pr < 4; ++pr) {
+              const int c = i * 8 + pr * 2;             // column inside the slab
+              const int t = (c & 31) >> 1;              // pair index inside the 32-column group
+              float lo = __uint_as_float(v[c]), hi = __uint_as_float(v[c + 1]);
+              if (EPI == EPI_BIAS_RELU) {
+                lo += sBias[j * 64 + c];
+                hi += sBias[j * 64 + c + 1];
+                asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                uint32_t gt;
+                asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(w[pr]), "r"(0u));
+                obits[c >> 5] |= gt & (0x00010001u << t);
+              } else {
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                const uint32_t sel = (mbits[2 * j + (c >> 5)] >> t) & 0x00010001u;
+                w[pr] &= sel * 0xFFFFu;
               }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = ((mbits[2 * j + (i >> 2)] >> ((i & 3) * 8 + e)) & 1u) ? f[e] : 0.f;
             }
-            *reinterpret_cast<uint4*>(addr) =
-                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            *reinterpret_cast<uint4*>(ob + sw_row + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
           if (EPI == EPI_BIAS_RELU && p.bits_out)
             *reinterpret_cast<uint2*>(p.bits_out + (size_t)(tile * kTileM + r) * p.bits_ld + (n0 + j * 64) / 32) =
                 make_uint2(obits[0], obits[1]);
           fence_proxy_async_smem();
-          named_bar_sync(2, 128);
-          if (leader) {
-            tma_store_2d(&tmOut, n0 + j * 64, tile * kTileM, ob);
+          named_bar_sync(2 + 2 * grp, 128);
+          if (gleader) {
+            tma_store_2d_hint(&tmOut, n0 + j * 64, tile * kTileM, ob, p.store_policy);
             bulk_commit();
           }
         }
@@ -212,7 +226,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
     }
-    if (kStaged && leader) bulk_wait<0>();
+    if (kStaged && gleader) bulk_wait<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -247,7 +261,7 @@ constexpr int kDwRows = 64;                 // pixel rows per stage
 constexpr int kDwSlab = kDwRows * 128;      // [64 rows x 64 cols] bf16
 
 template <int N_TILE>
-__global__ void __launch_bounds__(kThreads, 1) k_tc_dw(const __grid_constant__ DwJobs jobs) {
+__global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__ DwJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const DwJob& J = jobs.j[blockIdx.y];
