@@ -1,8 +1,11 @@
 // precision=bf16: the tensor-core path.  bf16 activations/weights, fp32 accumulation in TMEM (tcgen05.mma),
 // fp32 master weights and gradients.  Per layer: one k_tc_gemm launch forward, one for dX, one k_tc_dw for dW;
 // encodings, the 3-/1-wide output layers, losses and reductions are SIMT kernels.  No fallback to the fp32 path.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <string>
+#include <vector>
 
 #include "engine.cuh"
 #include "fp32_kernels.cuh"
@@ -319,6 +322,8 @@ struct BfChain {
   uint32_t* bits[MARF_MAX_LAYERS + 1] = {};  // bits[l]: 1-bit ReLU mask of act[l] (l >= 1), [chunk, ld[l]/32] words
   bf16* dY[MARF_MAX_LAYERS] = {};         // dY[l]: gradient wrt the output of layer l [chunk, np(l)] (kept for the dW pass)
   CUtensorMap tmDY128[MARF_MAX_LAYERS], tmDY64[MARF_MAX_LAYERS];
+  uint32_t* flags_fwd[MARF_MAX_LAYERS + 1] = {};   // flags_fwd[l]: per-tile completion counters of act[l] (written by layer l-1)
+  uint32_t* flags_bwd[MARF_MAX_LAYERS] = {};       // flags_bwd[l]: per-tile completion counters of dY[l] (written by dX of layer l+1)
   float* logits = nullptr;                // [chunk,4] fp32
   float* dlogits = nullptr;               // [chunk,4] fp32
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
@@ -330,6 +335,8 @@ struct Bf16State {
   BfChain img, msk;
   float* dX0 = nullptr;                   // [chunk, 64] fp32
   int num_sms = 148;
+  uint32_t* flags_all = nullptr;          // every per-tile flag array of both chains, zeroed before each chained launch
+  size_t flags_words = 0, flags_used = 0;
 };
 
 static int make_tmap(marf_handle* h, Bf16State* S, CUtensorMap* m, void* base, int rows, int cols_ld, int box_rows) {
@@ -386,7 +393,14 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     if (rc) return rc;
     if (l >= 1) {
       B.bits[l] = (uint32_t*)ws_alloc(h, (size_t)h->chunk * (B.ld[l] / 32) * 4);
-      if (!B.bits[l]) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (mask bits)");
+      B.flags_fwd[l] = S->flags_all + S->flags_used;
+      S->flags_used += h->chunk / 128 + 1;
+      if (!B.bits[l] || S->flags_used > S->flags_words) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (mask bits)");
+    }
+    if (l < F.n - 1) {
+      B.flags_bwd[l] = S->flags_all + S->flags_used;
+      S->flags_used += h->chunk / 128 + 1;
+      if (S->flags_used > S->flags_words) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (flags)");
     }
     if (l < F.n - 1) {
       B.dY[l] = (bf16*)ws_alloc(h, (size_t)h->chunk * B.L[l].np * 2);
@@ -430,6 +444,9 @@ int bf16_create(marf_handle* h) {
   cudaDeviceProp prop;
   BF_TRY(h, cudaGetDeviceProperties(&prop, h->cfg.device));
   S->num_sms = prop.multiProcessorCount;
+  S->flags_words = (size_t)(h->chunk / 128 + 1) * 4 * MARF_MAX_LAYERS;
+  S->flags_all = (uint32_t*)ws_alloc(h, S->flags_words * 4);
+  if (!S->flags_all) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (flags)");
   int rc = build_bf_chain(h, S, S->img, h->img, true);
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
@@ -452,73 +469,176 @@ bool bf16_supported(const marf_handle* h, const marf_step_io*, std::string* why)
 }
 
 // ------------------------------------------------------------------------------------------------ launches
-static int launch_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int l, int rows) {
-  Bf16State* S = h->bf16;
+// distribute the launch's CTAs over the jobs in proportion to `weight` (>= 1 CTA each), at most n_tiles per job
+static void assign_ctas(tc::GemmJobs& jobs, const int* weight, int num_sms) {
+  int wsum = 0;
+  for (int i = 0; i < jobs.n; ++i) wsum += weight[i];
+  int begin = 0, left = num_sms;
+  for (int i = 0; i < jobs.n; ++i) {
+    int c = std::max(1, (int)((long long)num_sms * weight[i] / wsum));
+    c = std::min(c, std::min(jobs.j[i].p.n_tiles, left - (jobs.n - 1 - i)));
+    jobs.j[i].cta_begin = begin;
+    jobs.j[i].cta_count = std::max(1, c);
+    begin += jobs.j[i].cta_count;
+    left -= jobs.j[i].cta_count;
+  }
+}
+
+static tc::GemmJob fwd_job(BfChain& B, int l, int rows, int n_tile, int n0) {
   BfLayer& L = B.L[l];
-  tc::GemmParams p{};
-  p.n_tiles = rows / 128;
-  p.k_chunks = L.kp / 64;
-  p.bias = B.f32->bp[l];
-  p.bits_out = B.bits[l + 1];
-  p.bits_ld = B.ld[l + 1] / 32;
-  p.reverse = l & 1;                         // alternate direction: start where the previous layer just finished
-  p.load_policy = tc::kEvictFirst;           // inputs are not read again before the backward pass
-  p.store_policy = tc::kEvictLast;           // outputs are the next launch's inputs
-  int n_tile = (L.kp > 256 && L.np > 128) ? 128 : std::min(L.np, 256);
-  dim3 grid(std::min(p.n_tiles, std::max(1, S->num_sms / (L.np / n_tile))), L.np / n_tile);
-  int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
-  if (n_tile == 256)
-    tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(B.tmAct128[l], L.tmWk, B.tmAct128[l + 1], B.tmAct128[l + 1], p);
-  else
-    tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(B.tmAct128[l], L.tmWk, B.tmAct128[l + 1], B.tmAct128[l + 1], p);
-  BF_LAUNCH(h);
+  tc::GemmJob J{};
+  J.tmA = B.tmAct128[l];
+  J.tmW = L.tmWk;
+  J.tmOut = B.tmAct128[l + 1];
+  J.p.n_tiles = rows / 128;
+  J.p.k_chunks = L.kp / 64;
+  J.p.bias = B.f32->bp[l];
+  J.p.bits_out = B.bits[l + 1];
+  J.p.bits_ld = B.ld[l + 1] / 32;
+  J.p.reverse = getenv("MARF_CHAIN") ? 0 : (l & 1);   // start where the previous launch just finished (still in L2)
+  J.p.load_policy = tc::kEvictFirst;           // inputs are not read again before the backward pass
+  J.p.prefetch_ahead = getenv("MARF_PREFETCH") ? atoi(getenv("MARF_PREFETCH")) : 0;
+  J.p.store_policy = tc::kEvictLast;           // outputs are the next launch's inputs
+  J.n0 = n0;
+  (void)n_tile;
+  return J;
+}
+
+// forward of every tensor-core layer of the given chains.  Layers whose input is wider than 256 (mask head layer 0)
+// run first as their own launch (N split in two 128-column jobs); all other layers of all chains share ONE launch
+// in which layer l+1 consumes layer l's tiles through per-tile flags (L2-resident hand-over).
+static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
+  Bf16State* S = h->bf16;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    for (int l = 0; l < B.n - 1; ++l) {
+      BfLayer& L = B.L[l];
+      if (!(L.kp > 256 && L.np > 128)) continue;
+      tc::GemmJobs jobs{};
+      int w[tc::kMaxGemmJobs];
+      for (int t = 0; t < L.np / 128; ++t) { jobs.j[jobs.n] = fwd_job(B, l, rows, 128, t * 128); w[jobs.n++] = 1; }
+      assign_ctas(jobs, w, S->num_sms);
+      int smem = tc::gemm_smem(128, L.kp / 64, true).total + 1024;
+      int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
+      tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+      BF_LAUNCH(h);
+    }
+  }
+  // Chained mode (MARF_CHAIN=1, experimental): every remaining layer of every chain in one launch, layer l+1 consuming
+  // layer l's tiles through per-tile flags.  Default: one launch per depth level (the same-depth layers of all chains
+  // share the SMs); measured faster on B200 because each launch then streams at the full HBM rate.
+  static const bool chain_mode = getenv("MARF_CHAIN") != nullptr;
+  int max_depth = 0;
+  for (int ci = 0; ci < n_chains; ++ci) max_depth = std::max(max_depth, chains[ci]->n - 1);
+  if (chain_mode) BF_TRY(h, cudaMemsetAsync(S->flags_all, 0, S->flags_used * 4, st));
+  // default: one layer per launch, chain after chain: a 110 MB output stays L2-resident for the next launch, which
+  // walks the tiles in the opposite direction (measured: faster than sharing a launch between the two chains)
+  for (int pass = 0; pass < (chain_mode ? 1 : max_depth * n_chains); ++pass) {
+    const int only_chain = pass / max_depth, level = pass % max_depth;
+    tc::GemmJobs jobs{};
+    int w[tc::kMaxGemmJobs];
+    int max_kc = 1;
+    for (int ci = 0; ci < n_chains; ++ci) {
+      BfChain& B = *chains[ci];
+      for (int l = 0; l < B.n - 1; ++l) {
+        if (!chain_mode && (l != level || ci != only_chain)) continue;
+        BfLayer& L = B.L[l];
+        if (L.kp > 256 && L.np > 128) continue;
+        if (L.np != 256) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: hidden width must be 256");
+        if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: too many layers");
+        tc::GemmJob J = fwd_job(B, l, rows, 256, 0);
+        if (chain_mode) {
+          const bool chained_in = l >= 1 && !(B.L[l - 1].kp > 256 && B.L[l - 1].np > 128);
+          J.flags_in = chained_in ? B.flags_fwd[l] : nullptr;
+          J.in_target = 2u;
+          J.flags_out = (l + 1 < B.n - 1) ? B.flags_fwd[l + 1] : nullptr;
+        }
+        w[jobs.n] = 1;                              // the epilogue (same for every layer) bounds a tile, not K
+        max_kc = std::max(max_kc, L.kp / 64);
+        jobs.j[jobs.n++] = J;
+      }
+    }
+    if (jobs.n == 0) continue;
+    assign_ctas(jobs, w, S->num_sms);
+    int smem = tc::gemm_smem(256, max_kc, true).total + 1024;
+    int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
+    tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+    BF_LAUNCH(h);
+  }
   return MARF_OK;
 }
 
-// dY[l-1] = (dY[l] W_l) * (act[l] > 0), l >= 1
-static int launch_dx(marf_handle* h, cudaStream_t st, BfChain& B, int l, int rows) {
+// dX of every tensor-core layer l >= 1 of the given chains in ONE launch (dY[l-1] = (dY[l] W_l) * relu_mask(act[l])),
+// chained through per-tile flags; then dX0 of the chains that need the gradient w.r.t. their input.
+static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
   Bf16State* S = h->bf16;
-  BfLayer& L = B.L[l];
-  tc::GemmParams p{};
-  p.n_tiles = rows / 128;
-  p.k_chunks = L.np / 64;                    // contraction over the layer's outputs
-  p.bits_in = B.bits[l];
-  p.bits_ld = B.ld[l] / 32;
-  p.reverse = l & 1;
-  p.load_policy = tc::kEvictFirst;
-  p.store_policy = tc::kEvictLast;
-  int n_total = L.kp;                        // produces the layer's (padded) inputs = np of layer l-1
-  int n_tile = std::min(n_total, 256);
-  if (n_total % n_tile) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: input width must tile by 256/128/64");
-  dim3 grid(std::min(p.n_tiles, std::max(1, S->num_sms / (n_total / n_tile))), n_total / n_tile);
-  int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
-  if (n_tile == 256)
-    tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[l], L.tmWt, B.tmDY128[l - 1], B.tmAct128[l], p);
-  else if (n_tile == 128)
-    tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[l], L.tmWt, B.tmDY128[l - 1], B.tmAct128[l], p);
-  else
-    return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: unsupported tile");
-  BF_LAUNCH(h);
-  return MARF_OK;
-}
-
-static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain& B, int rows) {
-  Bf16State* S = h->bf16;
-  BfLayer& L = B.L[0];
-  if (L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX0: encoded input must fit 64 columns");
-  tc::GemmParams p{};
-  p.n_tiles = rows / 128;
-  p.k_chunks = L.np / 64;
-  p.out_f32 = S->dX0;
-  p.ld_out = 64;
-  p.n_store = pad4(L.k_in);
-  p.reverse = 0;
-  p.load_policy = tc::kEvictFirst;
-  p.store_policy = tc::kEvictNormal;
-  dim3 grid(std::min(p.n_tiles, S->num_sms), 1);
-  int smem = tc::gemm_smem(64, p.k_chunks, false).total + 1024;
-  tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(B.tmDY128[0], L.tmWt, B.tmDY128[0], B.tmDY128[0], p);
-  BF_LAUNCH(h);
+  static const bool chain_mode = getenv("MARF_CHAIN") != nullptr;
+  int max_depth = 0;
+  for (int ci = 0; ci < n_chains; ++ci) max_depth = std::max(max_depth, chains[ci]->n - 1);
+  if (chain_mode) BF_TRY(h, cudaMemsetAsync(S->flags_all, 0, S->flags_used * 4, st));
+  for (int pass = 0; pass < (chain_mode ? 1 : max_depth * n_chains); ++pass) {
+    const int only_chain = pass / max_depth, level = max_depth - 1 - pass % max_depth;
+    tc::GemmJobs jobs{};
+    int w[tc::kMaxGemmJobs];
+    for (int ci = 0; ci < n_chains; ++ci) {
+      BfChain& B = *chains[ci];
+      for (int l = B.n - 2; l >= 1; --l) {
+        if (!chain_mode && (l != level || ci != only_chain)) continue;
+        BfLayer& L = B.L[l];
+        if (L.kp != 256 || L.np != 256) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: hidden width must be 256");
+        if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: too many layers");
+        tc::GemmJob J{};
+        J.tmA = B.tmDY128[l];
+        J.tmW = L.tmWt;
+        J.tmOut = B.tmDY128[l - 1];
+        J.p.n_tiles = rows / 128;
+        J.p.k_chunks = L.np / 64;
+        J.p.bits_in = B.bits[l];
+        J.p.bits_ld = B.ld[l] / 32;
+        J.p.reverse = chain_mode ? 0 : (l & 1);      // start where the previous launch just finished (still in L2)
+        J.p.load_policy = tc::kEvictFirst;         // (dY[l] is read again by the dW pass, but long after L2 has turned over)
+        J.p.store_policy = tc::kEvictLast;
+        J.n0 = 0;
+        if (chain_mode) {
+          J.flags_in = l < B.n - 2 ? B.flags_bwd[l] : nullptr;   // dY[n-2] comes from the output-layer kernel (complete)
+          J.in_target = 2u;
+          J.flags_out = l - 1 >= 1 ? B.flags_bwd[l - 1] : nullptr;
+        }
+        w[jobs.n] = 1;
+        jobs.j[jobs.n++] = J;
+      }
+    }
+    if (jobs.n == 0) continue;
+    assign_ctas(jobs, w, S->num_sms);
+    int smem = tc::gemm_smem(256, 4, true).total + 1024;
+    int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
+    tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
+    BF_LAUNCH(h);
+  }
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    if (!B.need_dx0) continue;
+    BfLayer& L = B.L[0];
+    if (L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX0: encoded input must fit 64 columns");
+    tc::GemmJobs one{};
+    one.n = 1;
+    tc::GemmJob& J = one.j[0];
+    J.tmA = B.tmDY128[0];
+    J.tmW = L.tmWt;
+    J.tmOut = B.tmDY128[0];
+    J.p.n_tiles = rows / 128;
+    J.p.k_chunks = L.np / 64;
+    J.p.out_f32 = S->dX0;
+    J.p.ld_out = 64;
+    J.p.n_store = pad4(L.k_in);
+    J.p.load_policy = tc::kEvictNormal;
+    J.p.store_policy = tc::kEvictNormal;
+    J.cta_begin = 0;
+    J.cta_count = std::min(J.p.n_tiles, S->num_sms);
+    int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
+    tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<J.cta_count, tc::kThreads, smem, st>>>(one);
+    BF_LAUNCH(h);
+  }
   return MARF_OK;
 }
 
@@ -610,26 +730,6 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   return MARF_OK;
 }
 
-static int bf_chain_forward(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* Wlast, const float* blast) {
-  for (int l = 0; l < B.n - 1; ++l) {
-    int rc = launch_fwd(h, st, B, l, rows);
-    if (rc) return rc;
-  }
-  return thin_fwd(h, st, B, rows, Wlast, blast);
-}
-
-// dX chain only (dY[l] for every tensor-core layer stays resident for launch_dw_all)
-static int bf_chain_backward_dx(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* Wlast) {
-  int rc = thin_bwd(h, st, B, rows, Wlast);      // -> dY[n-2]
-  if (rc) return rc;
-  for (int l = B.n - 2; l >= 1; --l) {
-    rc = launch_dx(h, st, B, l, rows);
-    if (rc) return rc;
-  }
-  if (B.need_dx0) rc = launch_dx0(h, st, B, rows);
-  return rc;
-}
-
 // one launch: bias (fp32) + bf16 forward / transposed weights of every tensor-core layer
 static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
   Bf16State* S = h->bf16;
@@ -711,16 +811,23 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
     else k_encode_bf16<0><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
   }
   BF_LAUNCH(h);
-  int rc = bf_chain_forward(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1], io->mlp_b[c.n_layers - 1]);
+  if (implicit && !(h->feats_valid && h->n_chunks == 1)) {
+    k_mask_features_bf16<<<rg.padded, 128, 0, st>>>(h->geo, rg, io->rgb, io->embed, c.mask_embed_dim, c.mask_uv_freqs,
+                                                    S->msk.act[0], S->msk.ld[0]);
+    BF_LAUNCH(h);
+    h->feats_valid = h->n_chunks == 1;
+  }
+  // chain after chain, each followed at once by its output layer: the last hidden activation is still in L2
+  BfChain* c_img[1] = {&S->img};
+  BfChain* c_msk[1] = {&S->msk};
+  int rc = launch_forward_all(h, st, c_img, 1, rg.padded);
+  if (rc) return rc;
+  rc = thin_fwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1], io->mlp_b[c.n_layers - 1]);
   if (rc) return rc;
   if (implicit) {
-    if (!(h->feats_valid && h->n_chunks == 1)) {
-      k_mask_features_bf16<<<rg.padded, 128, 0, st>>>(h->geo, rg, io->rgb, io->embed, c.mask_embed_dim, c.mask_uv_freqs,
-                                                      S->msk.act[0], S->msk.ld[0]);
-      BF_LAUNCH(h);
-      h->feats_valid = h->n_chunks == 1;
-    }
-    rc = bf_chain_forward(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1], io->mask_b[c.mask_n_layers - 1]);
+    rc = launch_forward_all(h, st, c_msk, 1, rg.padded);
+    if (rc) return rc;
+    rc = thin_fwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1], io->mask_b[c.mask_n_layers - 1]);
     if (rc) return rc;
   }
   if (stats) {
@@ -754,12 +861,18 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.dmlogits = implicit ? S->msk.dlogits : nullptr; ga.dmld = 4;
   k_loss_grad<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, ga, h->coef);
   BF_LAUNCH(h);
-  int rc = bf_chain_backward_dx(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
+  BfChain* c_img[1] = {&S->img};
+  BfChain* c_msk[1] = {&S->msk};
+  int rc = thin_bwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
+  if (rc) return rc;
+  rc = launch_dx_all(h, st, c_img, 1, rg.padded);
   if (rc) return rc;
   k_encode_backward<<<(rg.padded + 255) / 256, 256, 0, st>>>(h->geo, rg, h->Hm, S->dX0, 64, h->G);
   BF_LAUNCH(h);
   if (implicit) {
-    rc = bf_chain_backward_dx(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
+    rc = thin_bwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
+    if (rc) return rc;
+    rc = launch_dx_all(h, st, c_msk, 1, rg.padded);
     if (rc) return rc;
   }
   BfChain* chains[2] = {&S->img, &S->msk};
@@ -865,26 +978,44 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     if (N % n_tile) return MARF_ERR_INVALID;
     rc = make_tmap(&tmp, &S, &tA, dA, rows, K, 128);
     if (!rc) rc = make_tmap(&tmp, &S, &tW, dW, N, K, n_tile);
+    tc::GemmJobs jobs{};
+    jobs.n = N / n_tile;
     tc::GemmParams p{};
     p.n_tiles = rows / 128;
     p.k_chunks = K / 64;
     p.reverse = (rows / 128) & 1;
     p.load_policy = tc::kEvictFirst;
     p.store_policy = tc::kEvictLast;
-    dim3 grid(std::min(p.n_tiles, std::max(1, 148 / (N / n_tile))), N / n_tile);
+    const int per_job = std::min(p.n_tiles, std::max(1, 148 / jobs.n));
+    const int grid = per_job * jobs.n;
+    auto fill = [&](const CUtensorMap& a_, const CUtensorMap& w_, const CUtensorMap& o_) {
+      for (int t = 0; t < jobs.n; ++t) {
+        jobs.j[t].tmA = a_; jobs.j[t].tmW = w_; jobs.j[t].tmOut = o_; jobs.j[t].p = p; jobs.j[t].n0 = t * n_tile;
+        jobs.j[t].cta_begin = t * per_job; jobs.j[t].cta_count = per_job;
+      }
+    };
     if (mode == 2) {
       p.out_f32 = out; p.ld_out = 64; p.n_store = 64;
       int smem = tc::gemm_smem(64, p.k_chunks, false).total + 1024;
-      if (!rc) tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(tA, tW, tA, tA, p);
+      fill(tA, tW, tA);
+      if (!rc) tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(jobs);
     } else {
       if (cudaMalloc(&dOut, (size_t)rows * N * 2) != cudaSuccess) return MARF_ERR_CUDA;
       if (!rc) rc = make_tmap(&tmp, &S, &tO, dOut, rows, N, 128);
       int smem = tc::gemm_smem(n_tile, p.k_chunks, true).total + 1024;
+      long long* dTrace = nullptr;
+      const int n_iter_trace = (p.n_tiles + per_job - 1) / per_job;
+      if (mode == 0 && getenv("MARF_TC_TRACE")) {
+        cudaMalloc(&dTrace, (size_t)n_iter_trace * 16 * sizeof(long long));
+        cudaMemset(dTrace, 0, (size_t)n_iter_trace * 16 * sizeof(long long));
+        p.trace = dTrace;
+      }
       if (mode == 0) {
         p.bias = aux;
+        fill(tA, tW, tO);
         if (!rc) {
-          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
-          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
+          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
           else rc = MARF_ERR_INVALID;
         }
       } else {
@@ -893,9 +1024,10 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
         k_make_bits<<<(rows * (N / 32) + 255) / 256, 256, 0, st>>>(rows, N, aux, dBits);
         p.bits_in = dBits;
         p.bits_ld = N / 32;
+        fill(tA, tW, tO);
         if (!rc) {
-          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
-          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(tA, tW, tO, tO, p);
+          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
+          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
           else rc = MARF_ERR_INVALID;
         }
         cudaStreamSynchronize(st);
@@ -904,6 +1036,19 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
       if (!rc) {
         long long tot = (long long)rows * N;
         k_bf16_to_f32<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, dOut, out);
+      }
+      if (dTrace) {
+        cudaStreamSynchronize(st);
+        std::vector<long long> tr((size_t)n_iter_trace * 16);
+        cudaMemcpy(tr.data(), dTrace, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long t00 = tr[1];
+        fprintf(stderr, "trace (cycles rel. to first MMA start): iter | prod_issued mma_start mma_committed | g0: acc_full ld0 st0 ld1 st1 | g1: acc_full ld0 st0 ld1 st1\n");
+        for (int i = 0; i < n_iter_trace; ++i) {
+          fprintf(stderr, "%3d |", i);
+          for (int k = 0; k < 15; ++k) fprintf(stderr, " %7lld", tr[i * 16 + k] ? tr[i * 16 + k] - t00 : -1);
+          fprintf(stderr, "\n");
+        }
+        cudaFree(dTrace);
       }
     }
   } else if (mode == 3) {

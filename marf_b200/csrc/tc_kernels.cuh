@@ -37,6 +37,8 @@ struct GemmParams {
   int reverse;          // walk the tiles last-to-first (the previous layer's newest output is still in L2)
   unsigned long long load_policy;   // L2 cache hint of the streamed A tiles
   unsigned long long store_policy;  // L2 cache hint of the output tiles
+  int prefetch_ahead;   // tiles to prefetch into L2 ahead of the SMEM ring (0 = off)
+  long long* trace;     // diagnostics: per-tile clock64() stamps of CTA 0 ([tile_iter][16]); nullptr in production
 };
 
 struct GemmSmem {       // offsets computed on host and device identically
@@ -58,15 +60,47 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// One launch = several GEMM "jobs" (layers); a contiguous range of CTAs serves each job, persistent over its tiles.
+// Jobs may be chained: job B whose input is job A's output waits, tile by tile, on A's completion flags, so the
+// activations travel producer -> consumer through L2 instead of HBM (all CTAs of the launch are co-resident:
+// grid <= #SMs, 1 CTA/SM).
+struct GemmJob {
+  CUtensorMap tmA, tmW, tmOut;
+  GemmParams p;
+  int n0;                      // first output column of this job (N tiles of one layer are separate jobs)
+  int cta_begin, cta_count;    // CTAs [cta_begin, cta_begin+cta_count) of the launch work on this job
+  const uint32_t* flags_in;    // per-tile completion counters of the producer job (nullptr: input already complete)
+  uint32_t* flags_out;         // per-tile completion counters this job bumps (nullptr: nobody waits)
+  uint32_t in_target;          // flags_in[tile] >= in_target  <=>  the input tile is complete
+};
+constexpr int kMaxGemmJobs = 8;
+struct GemmJobs { GemmJob j[kMaxGemmJobs]; int n; };
+
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <int N_TILE, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
-k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-          const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmMask, GemmParams p) {
+__global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__ GemmJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr bool kStaged = EPI != EPI_PLAIN_F32;
   constexpr int kSlabs = N_TILE / 64;
   constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
+  int jr = 0;
+  for (int i = 1; i < jobs.n; ++i)
+    if ((int)blockIdx.x >= jobs.j[i].cta_begin) jr = i;
+  const GemmJob& J = jobs.j[jr];
+  const GemmParams& p = J.p;
+  const int bid = (int)blockIdx.x - J.cta_begin;
+  const int nctas = J.cta_count;
+  if (bid >= nctas) return;                          // (grid padded: not used)
   const GemmSmem L = gemm_smem(N_TILE, p.k_chunks, kStaged);
   uint8_t* sW = smem;
   uint8_t* sA = smem + L.a_off;
@@ -78,19 +112,18 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   uint64_t* w_full = bars + 2 * kStages;
   uint64_t* acc_full = w_full + 1;       // [2]
   uint64_t* acc_empty = acc_full + 2;    // [2]
-  uint64_t* mask_full = acc_empty + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_full + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * N_TILE;
+  const int n0 = J.n0;
 
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmW);
-    if (kStaged) prefetch_tmap(&tmOut);
+    prefetch_tmap(&J.tmA);
+    prefetch_tmap(&J.tmW);
+    if (kStaged) prefetch_tmap(&J.tmOut);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); mbar_init(&mask_full[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -105,16 +138,38 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
-      for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &tmW, c * kChunkK, n0, w_full);
+      for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &J.tmW, c * kChunkK, n0, w_full);
       uint32_t it = 0;
-      for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x) {
+      const int kAhead = p.prefetch_ahead;           // tiles prefetched into L2 ahead of the SMEM ring (0: off)
+      if (!J.flags_in && kAhead > 0)
+        for (int a = 0; a < kAhead; ++a) {
+          const int tp = bid + a * nctas;
+          if (tp < p.n_tiles)
+            for (int c = 0; c < p.k_chunks; ++c) tma_prefetch_2d(&J.tmA, c * kChunkK, (p.reverse ? p.n_tiles - 1 - tp : tp) * kTileM);
+        }
+      for (int t0 = bid; t0 < p.n_tiles; t0 += nctas) {
         const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
+        if (!J.flags_in && kAhead > 0) {
+          const int tp = t0 + kAhead * nctas;
+          if (tp < p.n_tiles)
+            for (int c = 0; c < p.k_chunks; ++c) tma_prefetch_2d(&J.tmA, c * kChunkK, (p.reverse ? p.n_tiles - 1 - tp : tp) * kTileM);
+        }
+        if (J.flags_in) {
+          // wait until the producer job has finished this tile (bounded: a protocol bug traps instead of hanging)
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(J.flags_in + tile) < J.in_target) {
+            __nanosleep(64);
+            if (++spins > (1u << 22)) __trap();
+          }
+          fence_proxy_async_all();                   // order the acquire before the async-proxy (TMA) reads
+        }
         for (int c = 0; c < p.k_chunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], kChunkBytes);
-          tma_load_2d_hint(sA + s * kChunkBytes, &tmA, c * kChunkK, tile * kTileM, &full[s], p.load_policy);
+          tma_load_2d_hint(sA + s * kChunkBytes, &J.tmA, c * kChunkK, tile * kTileM, &full[s], p.load_policy);
         }
+        if (p.trace && bid == 0) p.trace[(t0 / nctas) * 16 + 0] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -124,10 +179,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       mbar_wait(w_full, 0);
       tc_fence_after();
       uint32_t it = 0, t_iter = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_iter) {
+      for (int t0 = bid; t0 < p.n_tiles; t0 += nctas, ++t_iter) {
         const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
         mbar_wait(&acc_empty[a], aph ^ 1);
         tc_fence_after();
+        if (p.trace && bid == 0) p.trace[t_iter * 16 + 1] = clock64();
         const uint32_t d_tmem = tmem_base + a * N_TILE;
         for (int c = 0; c < p.k_chunks; ++c, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
@@ -140,6 +196,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           umma_commit(&empty[s]);
         }
         umma_commit(&acc_full[a]);
+        if (p.trace && bid == 0) p.trace[t_iter * 16 + 2] = clock64();
       }
     }
   } else {
@@ -151,8 +208,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool gleader = threadIdx.x == 64 + 128 * grp;
     const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
     uint8_t* ob = sOut + grp * kChunkBytes;
+    constexpr int kLastSlabOfGroup0 = ((kSlabs - 1) & 1) == 0 ? kSlabs - 1 : kSlabs - 2;
+    constexpr int kLastSlabOfGroup1 = ((kSlabs - 1) & 1) == 1 ? kSlabs - 1 : kSlabs - 2;
+    constexpr int kGroupSlabs = kSlabs >= 2 ? kSlabs / 2 : 1;      // stores a group commits per tile
+    // flags_out[tile] receives +1 from every group that stores slabs of the tile (2 groups when kSlabs >= 2)
+    int pending_tile = -1;                             // tile whose stores are committed but not yet signalled
     uint32_t t_iter = 0;
-    for (int t0 = blockIdx.x; t0 < p.n_tiles; t0 += gridDim.x, ++t_iter) {
+    for (int t0 = bid; t0 < p.n_tiles; t0 += nctas, ++t_iter) {
       const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
       const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
       uint32_t mbits[2 * kSlabs];
@@ -163,6 +225,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
+      const bool tr = p.trace && bid == 0 && (threadIdx.x == 64 || threadIdx.x == 192);
+      if (tr) p.trace[t_iter * 16 + 3 + grp * 6] = clock64();
 #pragma unroll
       for (int j = 0; j < kSlabs; ++j) {
         if ((j & 1) != grp) continue;
@@ -179,6 +243,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           named_bar_sync(1 + 2 * grp, 128);
         }
         tmem_ld_wait();
+        if (tr) p.trace[t_iter * 16 + 4 + grp * 6 + (j >> 1) * 2] = clock64();
         if (EPI == EPI_PLAIN_F32) {
           float* o = p.out_f32 + (size_t)(tile * kTileM + r) * p.ld_out + n0 + j * 64;
 #pragma unroll
@@ -191,14 +256,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             uint32_t w[4];
+            float bv[8];
+            if (EPI == EPI_BIAS_RELU) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + j * 64 + i * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + j * 64 + i * 8 + 4);
+              bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+            }
 #pragma unroll
             for (int pr = 0; pr < 4; ++pr) {
               const int c = i * 8 + pr * 2;             // column inside the slab
               const int t = (c & 31) >> 1;              // pair index inside the 32-column group
               float lo = __uint_as_float(v[c]), hi = __uint_as_float(v[c + 1]);
               if (EPI == EPI_BIAS_RELU) {
-                lo += sBias[j * 64 + c];
-                hi += sBias[j * 64 + c + 1];
+                lo += bv[pr * 2];
+                hi += bv[pr * 2 + 1];
                 asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
                 uint32_t gt;
                 asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(w[pr]), "r"(0u));
@@ -216,9 +287,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 make_uint2(obits[0], obits[1]);
           fence_proxy_async_smem();
           named_bar_sync(2 + 2 * grp, 128);
+          if (tr) p.trace[t_iter * 16 + 5 + grp * 6 + (j >> 1) * 2] = clock64();
           if (gleader) {
-            tma_store_2d_hint(&tmOut, n0 + j * 64, tile * kTileM, ob, p.store_policy);
+            tma_store_2d_hint(&J.tmOut, n0 + j * 64, tile * kTileM, ob, p.store_policy);
             bulk_commit();
+            if (J.flags_out && j == (grp == 0 ? kLastSlabOfGroup0 : kLastSlabOfGroup1)) {
+              // lagged signalling: a TMA store needs ~3k cycles to complete, so the tile finished ONE tile ago is
+              // published now: everything except this tile's own stores (kGroupSlabs newest groups) has completed
+              if (pending_tile >= 0) {
+                bulk_wait<kGroupSlabs>();
+                fence_proxy_async_all();
+                red_release_gpu_add(J.flags_out + pending_tile, 1u);
+              }
+              pending_tile = tile;
+            }
           }
         }
       }
@@ -226,7 +308,13 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
     }
-    if (kStaged && gleader) bulk_wait<0>();
+    if (kStaged && gleader) {
+      bulk_wait<0>();
+      if (J.flags_out && pending_tile >= 0) {
+        fence_proxy_async_all();
+        red_release_gpu_add(J.flags_out + pending_tile, 1u);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();

@@ -84,6 +84,11 @@ __device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* m, int c0, 
                "r"(c0), "r"(c1), "r"(smem_u32(smem_src)), "l"(policy)
                : "memory");
 }
+// pull a tile into L2 ahead of the TMA load that will consume it (no SMEM involved)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
