@@ -226,10 +226,10 @@ static int sgemm(marf_handle* h, cudaStream_t st, int M, int N, int K, const flo
   if (M <= 0 || N <= 0 || K <= 0) return MARF_OK;
   if (N <= 16) {
     dim3 grid((M + GBM - 1) / GBM, (N + 15) / 16, k_split);
-    k_sgemm<A_KC, B_KC, 1, EPI><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, k_split);
+    launch_k(k_sgemm<A_KC, B_KC, 1, EPI>, grid, 256, 0, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, k_split);
   } else {
     dim3 grid((M + GBM - 1) / GBM, (N + 127) / 128, k_split);
-    k_sgemm<A_KC, B_KC, 8, EPI><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, k_split);
+    launch_k(k_sgemm<A_KC, B_KC, 8, EPI>, grid, 256, 0, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux, k_split);
   }
   LAUNCH_CHECK(h);
   return MARF_OK;
@@ -247,9 +247,9 @@ static int pack_chain(marf_handle* h, cudaStream_t st, Chain& C, const float* co
   for (int l = 0; l < C.n; ++l) {
     if (!W[l] || !b[l]) return fail(h, MARF_ERR_INVALID, "null layer parameter");
     int tot = C.ld_out[l] * C.ld_in[l];
-    k_pack<<<(tot + 255) / 256, 256, 0, st>>>(W[l], C.k_out[l], C.k_in[l], C.Wp[l], C.ld_out[l], C.ld_in[l]);
+    launch_k(k_pack, (tot + 255) / 256, 256, 0, st, W[l], C.k_out[l], C.k_in[l], C.Wp[l], C.ld_out[l], C.ld_in[l]);
     LAUNCH_CHECK(h);
-    k_pack<<<(C.ld_out[l] + 255) / 256, 256, 0, st>>>(b[l], 1, C.k_out[l], C.bp[l], 1, C.ld_out[l]);
+    launch_k(k_pack, (C.ld_out[l] + 255) / 256, 256, 0, st, b[l], 1, C.k_out[l], C.bp[l], 1, C.ld_out[l]);
     LAUNCH_CHECK(h);
   }
   return MARF_OK;
@@ -259,9 +259,9 @@ static int unpack_chain(marf_handle* h, cudaStream_t st, Chain& C, float* const*
   if (!gW || !gb) return fail(h, MARF_ERR_INVALID, "missing gradient pointers");
   for (int l = 0; l < C.n; ++l) {
     int tot = C.k_out[l] * C.k_in[l];
-    k_unpack<<<(tot + 255) / 256, 256, 0, st>>>(C.gWp[l], C.ld_in[l], gW[l], C.k_out[l], C.k_in[l]);
+    launch_k(k_unpack, (tot + 255) / 256, 256, 0, st, C.gWp[l], C.ld_in[l], gW[l], C.k_out[l], C.k_in[l]);
     LAUNCH_CHECK(h);
-    k_unpack<<<(C.k_out[l] + 255) / 256, 256, 0, st>>>(C.gbp[l], C.ld_out[l], gb[l], 1, C.k_out[l]);
+    launch_k(k_unpack, (C.k_out[l] + 255) / 256, 256, 0, st, C.gbp[l], C.ld_out[l], gb[l], 1, C.k_out[l]);
     LAUNCH_CHECK(h);
   }
   return MARF_OK;
@@ -278,7 +278,7 @@ static int chain_forward(marf_handle* h, cudaStream_t st, Chain& C, int M) {
     if (rc) return rc;
     if (!last && (C.skip_mask & (1u << (l + 1)))) {
       long long tot = (long long)M * C.d_in;
-      k_copy_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, C.d_in, C.act[0], C.ld_in[0], 0, C.act[l + 1],
+      launch_k(k_copy_cols, (unsigned)((tot + 255) / 256), 256, 0, st, M, C.d_in, C.act[0], C.ld_in[0], 0, C.act[l + 1],
                                                                  C.ld_in[l + 1], C.k_out[l], 0);
       LAUNCH_CHECK(h);
     }
@@ -305,7 +305,7 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
     {
       int rpb = std::max(256, (M + 63) / 64);
       dim3 grid((C.ld_out[l] + 31) / 32, (M + rpb - 1) / rpb);
-      k_colsum<<<grid, 256, 0, st>>>(M, C.ld_out[l], cur, ldy, C.gbp[l], rpb);
+      launch_k(k_colsum, grid, 256, 0, st, M, C.ld_out[l], cur, ldy, C.gbp[l], rpb);
       LAUNCH_CHECK(h);
     }
     if (l == 0 && !C.need_dx0) break;
@@ -315,7 +315,7 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
       if (rc) return rc;
       if (C.skip_mask) {
         long long tot = (long long)M * C.d_in;
-        k_copy_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, C.d_in, h->dX0acc, C.ld_in[0], 0, nxt, C.ld_in[0], 0, 1);
+        launch_k(k_copy_cols, (unsigned)((tot + 255) / 256), 256, 0, st, M, C.d_in, h->dX0acc, C.ld_in[0], 0, nxt, C.ld_in[0], 0, 1);
         LAUNCH_CHECK(h);
       }
     } else if (C.skip_mask & (1u << l)) {
@@ -323,11 +323,11 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
                                          C.ld_in[l], nullptr, 0, 1);
       if (rc) return rc;
       long long tot = (long long)M * C.k_out[l - 1];
-      k_relu_mask<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, C.k_out[l - 1], h->dXscratch, C.ld_in[l], C.act[l],
+      launch_k(k_relu_mask, (unsigned)((tot + 255) / 256), 256, 0, st, M, C.k_out[l - 1], h->dXscratch, C.ld_in[l], C.act[l],
                                                                  C.ld_in[l], nxt, C.ld_out[l - 1]);
       LAUNCH_CHECK(h);
       tot = (long long)M * C.d_in;
-      k_copy_cols<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(M, C.d_in, h->dXscratch, C.ld_in[l], C.k_out[l - 1],
+      launch_k(k_copy_cols, (unsigned)((tot + 255) / 256), 256, 0, st, M, C.d_in, h->dXscratch, C.ld_in[l], C.k_out[l - 1],
                                                                  h->dX0acc, C.ld_in[0], 0, 1);
       LAUNCH_CHECK(h);
     } else {
@@ -370,10 +370,10 @@ static int refresh_data(marf_handle* h, const marf_step_io* io, cudaStream_t st)
   h->feats_valid = false;
   CUDA_TRY(h, cudaMemsetAsync(h->sums_static, 0, 4 * sizeof(double), st));
   if (h->cfg.mask_mode == MARF_MASK_DISK) {
-    k_sum_f32<<<296, 256, 0, st>>>(io->masks, h->n_local, 3.0, h->sums_static + 0);
+    launch_k(k_sum_f32, 296, 256, 0, st, io->masks, h->n_local, 3.0, h->sums_static + 0);
     LAUNCH_CHECK(h);
     if (io->masks_eroded) {
-      k_sum_f32<<<296, 256, 0, st>>>(io->masks_eroded, h->n_local, 3.0, h->sums_static + 1);
+      launch_k(k_sum_f32, 296, 256, 0, st, io->masks_eroded, h->n_local, 3.0, h->sums_static + 1);
       LAUNCH_CHECK(h);
     }
   }
@@ -382,13 +382,13 @@ static int refresh_data(marf_handle* h, const marf_step_io* io, cudaStream_t st)
 
 static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st, int ci, bool stats) {
   PxRange rg = chunk_range(h, ci);
-  k_encode<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, h->Hm, 0, h->img.act[0], h->img.ld_in[0]);
+  launch_k(k_encode, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, h->Hm, 0, h->img.act[0], h->img.ld_in[0]);
   LAUNCH_CHECK(h);
   int rc = chain_forward(h, st, h->img, rg.padded);
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
     if (!(h->feats_valid && h->n_chunks == 1)) {
-      k_mask_features<<<rg.padded, 128, 0, st>>>(h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_uv_freqs,
+      launch_k(k_mask_features, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_uv_freqs,
                                                  h->msk.act[0], h->msk.ld_in[0]);
       LAUNCH_CHECK(h);
       h->feats_valid = h->n_chunks == 1;
@@ -405,7 +405,7 @@ static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-    k_loss_stats<<<std::min((rg.padded + 255) / 256, 592), 256, 0, st>>>(h->geo, rg, a, io->loss_sums);
+    launch_k(k_loss_stats, std::min((rg.padded + 255) / 256, 592), 256, 0, st, h->geo, rg, a, io->loss_sums);
     LAUNCH_CHECK(h);
   }
   return MARF_OK;
@@ -416,16 +416,16 @@ static int edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const float* pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
   double* ep = io->edge_pred ? io->edge_pred : h->edge_pred;
   long long tot = h->n_local * 3;
-  k_sobel_mag<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
+  launch_k(k_sobel_mag, (unsigned)((tot + 255) / 256), 256, 0, st, pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
   LAUNCH_CHECK(h);
-  k_gauss5<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h->edge_mag, c.batch * 3, c.rows, h->w, ep);
+  launch_k(k_gauss5, (unsigned)((tot + 255) / 256), 256, 0, st, h->edge_mag, c.batch * 3, c.rows, h->w, ep);
   LAUNCH_CHECK(h);
   EdgeArgs e;
   e.mask_mode = c.mask_mode;
   e.edge_pred = ep; e.edge_label = io->edges; e.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   e.masks_eroded = io->masks_eroded;
   e.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-  k_edge_stats<<<(unsigned)((h->n_local + 255) / 256), 256, 0, st>>>(h->geo, h->n_local, e, io->loss_sums);
+  launch_k(k_edge_stats, (unsigned)((h->n_local + 255) / 256), 256, 0, st, h->geo, h->n_local, e, io->loss_sums);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -447,17 +447,17 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   // the mask head's last-layer gradient is staged in its own logits buffer's twin: reuse dYb tail is unsafe,
   // so it is written after the image chain has consumed dYa (two launches of the same kernel).
   ga.dmlogits = nullptr; ga.dmld = 0;
-  k_loss_grad<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, ga, h->coef);
+  launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
   LAUNCH_CHECK(h);
   float* dx0 = nullptr;
   int rc = chain_backward(h, st, h->img, rg.padded, &dx0);
   if (rc) return rc;
-  k_encode_backward<<<(rg.padded + 255) / 256, 256, 0, st>>>(h->geo, rg, h->Hm, dx0, h->img.ld_in[0], h->G);
+  launch_k(k_encode_backward, (rg.padded + 255) / 256, 256, 0, st, h->geo, rg, h->Hm, dx0, h->img.ld_in[0], h->G);
   LAUNCH_CHECK(h);
   if (implicit) {
     ga.dlogits = h->dYb;                       // scratch (ignored)
     ga.dmlogits = h->dYa; ga.dmld = h->msk.ld_out[h->msk.n - 1];
-    k_loss_grad<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, ga, h->coef);
+    launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
     LAUNCH_CHECK(h);
     rc = chain_backward(h, st, h->msk, rg.padded, nullptr);
     if (rc) return rc;
@@ -478,7 +478,7 @@ static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, b
       if (rc) return rc;
     }
   }
-  k_sl3_to_SL3<<<h->cfg.batch_global, 64, 0, st>>>(io->warp, h->cfg.batch_global, h->Hm);
+  launch_k(k_sl3_to_SL3, h->cfg.batch_global, 64, 0, st, io->warp, h->cfg.batch_global, h->Hm);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -495,7 +495,7 @@ static int begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t s
 static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack = true) {
   if (!io->g_warp) return fail(h, MARF_ERR_INVALID, "missing g_warp");
   CUDA_TRY(h, cudaMemsetAsync(io->g_warp, 0, (size_t)h->cfg.batch_global * 8 * sizeof(float), st));
-  k_sl3_backward<<<h->cfg.batch, 64, 0, st>>>(io->warp, h->G, h->cfg.patch_offset, h->cfg.batch, io->g_warp);
+  launch_k(k_sl3_backward, h->cfg.batch, 64, 0, st, io->warp, h->G, h->cfg.patch_offset, h->cfg.batch, io->g_warp);
   LAUNCH_CHECK(h);
   if (!unpack) return MARF_OK;
   int rc = unpack_chain(h, st, h->img, io->g_mlp_w, io->g_mlp_b);
@@ -530,7 +530,7 @@ static int fp32_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st)
 static int fp32_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   int rc = begin_backward(h, io, st, nullptr);
   if (rc) return rc;
-  k_loss_coef<<<1, 1, 0, st>>>(io->loss_sums, io->norm_rgb, io->norm_edge, h->cfg.use_edges, h->coef);
+  launch_k(k_loss_coef, 1, 1, 0, st, io->loss_sums, io->norm_rgb, io->norm_edge, h->cfg.use_edges, h->coef);
   LAUNCH_CHECK(h);
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     if (!h->acts_valid) {
@@ -590,7 +590,7 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
   g.x0 = io->crop ? c.W / 2 - c.patch_W / 2 : 0;
   g.rows = g.h; g.row_offset = 0; g.patch_offset = 0;
   if (io->warp) {
-    k_sl3_to_SL3<<<io->n_patches, 64, 0, st>>>(io->warp, io->n_patches, h->Hm);
+    launch_k(k_sl3_to_SL3, io->n_patches, 64, 0, st, io->warp, io->n_patches, h->Hm);
     LAUNCH_CHECK(h);
   }
   long long n = (long long)io->n_patches * g.h * g.w;
@@ -599,11 +599,11 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
     rg.first = first;
     rg.count = (int)std::min<long long>(h->render_rows, n - first);
     rg.padded = (int)round_up(rg.count, 128);
-    k_encode<<<(rg.padded + 127) / 128, 128, 0, st>>>(g, rg, h->Hm, io->warp ? 0 : 1, h->img.act[0], h->img.ld_in[0]);
+    launch_k(k_encode, (rg.padded + 127) / 128, 128, 0, st, g, rg, h->Hm, io->warp ? 0 : 1, h->img.act[0], h->img.ld_in[0]);
     LAUNCH_CHECK(h);
     rc = chain_forward(h, st, h->img, rg.padded);
     if (rc) return rc;
-    k_sigmoid_out<<<(rg.count + 255) / 256, 256, 0, st>>>(rg.count, h->img.act[h->img.n], h->img.ld_out[h->img.n - 1],
+    launch_k(k_sigmoid_out, (rg.count + 255) / 256, 256, 0, st, rg.count, h->img.act[h->img.n], h->img.ld_out[h->img.n - 1],
                                                           io->rgb + first * 3);
     LAUNCH_CHECK(h);
   }
@@ -615,7 +615,7 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
 extern "C" int marf_sl3_to_SL3(marf_handle* h, const float* warp, int32_t n, float* out9, void* stream) {
   if (!h) return MARF_ERR_INVALID;
   if (!warp || !out9 || n <= 0) return fail(h, MARF_ERR_INVALID, "bad sl3 args");
-  k_sl3_to_SL3<<<n, 64, 0, (cudaStream_t)stream>>>(warp, n, out9);
+  launch_k(k_sl3_to_SL3, n, 64, 0, (cudaStream_t)stream, warp, n, out9);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -624,11 +624,11 @@ extern "C" int marf_warp_corners(marf_handle* h, const float* warp, int32_t n, f
   if (!h) return MARF_ERR_INVALID;
   if (!warp || !out || n <= 0 || n > h->cfg.batch_global) return fail(h, MARF_ERR_INVALID, "bad corner args");
   cudaStream_t st = (cudaStream_t)stream;
-  k_sl3_to_SL3<<<n, 64, 0, st>>>(warp, n, h->Hm);
+  launch_k(k_sl3_to_SL3, n, 64, 0, st, warp, n, h->Hm);
   LAUNCH_CHECK(h);
   Geo g = h->geo;
   g.h = h->cfg.patch_H; g.w = h->cfg.patch_W;
-  k_warp_corners<<<(n * 4 + 63) / 64, 64, 0, st>>>(g, h->Hm, n, out);
+  launch_k(k_warp_corners, (n * 4 + 63) / 64, 64, 0, st, g, h->Hm, n, out);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
@@ -639,6 +639,7 @@ constexpr int kMaxAdam = 40;
 struct AdamTable { AdamEntry e[kMaxAdam]; float beta1, beta2, eps, bc1, bc2_sqrt; };
 
 __global__ void k_adam(const __grid_constant__ AdamTable t) {
+  pdl_wait();
   const AdamEntry& E = t.e[blockIdx.y];
   const float step_size = E.lr / t.bc1;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < E.n; i += (long long)gridDim.x * blockDim.x) {
@@ -670,13 +671,14 @@ extern "C" int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stre
   t.bc1 = (float)(1.0 - pow((double)io->beta1, (double)io->step));
   t.bc2_sqrt = (float)sqrt(1.0 - pow((double)io->beta2, (double)io->step));
   dim3 grid((unsigned)std::min<long long>((max_n + 255) / 256, 64), io->n_tensors);
-  k_adam<<<grid, 256, 0, (cudaStream_t)stream>>>(t);
+  launch_k(k_adam, grid, 256, 0, (cudaStream_t)stream, t);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
 
 __global__ void k_warp_points(const float* __restrict__ xy, const float* __restrict__ Hm, int n, int p,
                               float* __restrict__ out) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n * p) return;
   int b = (int)(i / p);
@@ -693,10 +695,10 @@ extern "C" int marf_warp_points(marf_handle* h, const float* xy, const float* wa
   cudaStream_t st = (cudaStream_t)stream;
   float* Hm = nullptr;
   CUDA_TRY(h, cudaMallocAsync((void**)&Hm, (size_t)n * 9 * sizeof(float), st));
-  k_sl3_to_SL3<<<n, 64, 0, st>>>(warp, n, Hm);
+  launch_k(k_sl3_to_SL3, n, 64, 0, st, warp, n, Hm);
   LAUNCH_CHECK(h);
   long long tot = (long long)n * p;
-  k_warp_points<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(xy, Hm, n, p, out);
+  launch_k(k_warp_points, (unsigned)((tot + 255) / 256), 256, 0, st, xy, Hm, n, p, out);
   LAUNCH_CHECK(h);
   CUDA_TRY(h, cudaFreeAsync(Hm, st));
   return MARF_OK;
@@ -710,9 +712,9 @@ extern "C" int marf_compute_edges(marf_handle* h, const float* images, int32_t n
   long long tot = (long long)n * c * rows * w;
   double* mag = nullptr;
   CUDA_TRY(h, cudaMallocAsync((void**)&mag, tot * sizeof(double), st));
-  k_sobel_mag<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(images, n, c, rows, w, 0, mag);
+  launch_k(k_sobel_mag, (unsigned)((tot + 255) / 256), 256, 0, st, images, n, c, rows, w, 0, mag);
   LAUNCH_CHECK(h);
-  k_gauss5<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(mag, n * c, rows, w, out);
+  launch_k(k_gauss5, (unsigned)((tot + 255) / 256), 256, 0, st, mag, n * c, rows, w, out);
   LAUNCH_CHECK(h);
   CUDA_TRY(h, cudaFreeAsync(mag, st));
   return MARF_OK;

@@ -30,6 +30,7 @@ using bf16 = __nv_bfloat16;
 // ------------------------------------------------------------------------------------------------ SIMT helpers
 template <int LT>   // LT > 0: compile-time band count (registers); LT == 0: runtime g.L (local array)
 __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, bf16* __restrict__ X0, int ld) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
   uint4* o = reinterpret_cast<uint4*>(X0 + (size_t)t * ld);
@@ -65,6 +66,7 @@ __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, b
 // mask-head features (model/planar.py:342-349) in bf16, one block per pixel row
 __global__ void k_mask_features_bf16(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
                                      int embed_dim, int n_freqs, bf16* __restrict__ F, int ld) {
+  pdl_wait();
   int t = blockIdx.x;
   bf16* o = F + (size_t)t * ld;
   if (t >= rg.count) {
@@ -101,6 +103,7 @@ __global__ void k_mask_features_bf16(Geo g, PxRange rg, const float* __restrict_
 // W fp32 [rows, cols] -> bf16 [prow, pcol] (zero padded), optionally transposed: out[c][r]
 __global__ void k_pack_bf16(const float* __restrict__ W, int rows, int cols, bf16* __restrict__ out, int prow, int pcol,
                             int transpose) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= prow * pcol) return;
   int pr = i / pcol, pc = i - pr * pcol;
@@ -113,6 +116,7 @@ __global__ void k_pack_bf16(const float* __restrict__ W, int rows, int cols, bf1
 template <int OUT, int KCH>
 __global__ void k_thin_fwd(int n, const bf16* __restrict__ X, int ld, const float* __restrict__ W,
                            const float* __restrict__ bias, float* __restrict__ out) {
+  pdl_wait();
   const int width = KCH * 256;
   const int lane = threadIdx.x & 31;
   float w[KCH][OUT][8];
@@ -172,6 +176,7 @@ __global__ void k_thin_fwd(int n, const bf16* __restrict__ X, int ld, const floa
 template <int OUT>
 __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const float* __restrict__ W,
                           const uint32_t* __restrict__ bits, int bits_ld, bf16* __restrict__ dY, int ldy) {
+  pdl_wait();
   const int per_row = width / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int total_threads = gridDim.x * blockDim.x;         // multiple of per_row (host guarantees)
@@ -201,6 +206,7 @@ __global__ void k_thin_dx(int n, int width, const float* __restrict__ dl, const 
 
 // bit c of row = (X[row,c] > 0)   (diagnostics: builds the mask the forward epilogue would have written)
 static __global__ void k_make_bits(int rows, int width, const float* __restrict__ X, uint32_t* __restrict__ bits) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int words = width / 32;
   if (i >= rows * words) return;
@@ -215,6 +221,7 @@ static __global__ void k_make_bits(int rows, int width, const float* __restrict_
 template <int OUT>
 __global__ void k_thin_dw(int n, int width, const float* __restrict__ dl, const bf16* __restrict__ X, int ld,
                           float* __restrict__ dW, int ldw, float* __restrict__ db, int rows_per_block) {
+  pdl_wait();
   extern __shared__ float red[];      // [blockDim.y][OUT*width + OUT]
   const int kq = threadIdx.x * 8;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
@@ -268,6 +275,7 @@ __global__ void k_thin_dw(int n, int width, const float* __restrict__ dl, const 
 }
 
 static __global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, float* __restrict__ out) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __bfloat162float(in[i]);
 }
@@ -277,6 +285,7 @@ struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode
 constexpr int kMaxPack = 48;
 struct PackTable { PackEntry e[kMaxPack]; int n; };
 static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
+  pdl_wait();
   const PackEntry& E = t.e[blockIdx.y];
   const int tot = E.prow * E.pcol;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
@@ -290,6 +299,7 @@ static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
 struct UnpackEntry { const float* src; float* dst; int rows, cols, pcol; };
 struct UnpackTable { UnpackEntry e[kMaxPack]; int n; };
 static __global__ void k_unpack_table(const __grid_constant__ UnpackTable t) {
+  pdl_wait();
   const UnpackEntry& E = t.e[blockIdx.y];
   const int tot = E.rows * E.cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
@@ -520,7 +530,7 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
       assign_ctas(jobs, w, S->num_sms);
       int smem = tc::gemm_smem(128, L.kp / 64, true).total + 1024;
       int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
-      tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+      launch_k(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
       BF_LAUNCH(h);
     }
   }
@@ -562,7 +572,7 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
     assign_ctas(jobs, w, S->num_sms);
     int smem = tc::gemm_smem(256, max_kc, true).total + 1024;
     int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
-    tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+    launch_k(tc::k_tc_gemm<256, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -612,7 +622,7 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     assign_ctas(jobs, w, S->num_sms);
     int smem = tc::gemm_smem(256, 4, true).total + 1024;
     int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
-    tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
+    launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, grid, tc::kThreads, smem, st, jobs);
     BF_LAUNCH(h);
   }
   for (int ci = 0; ci < n_chains; ++ci) {
@@ -636,7 +646,7 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     J.cta_begin = 0;
     J.cta_count = std::min(J.p.n_tiles, S->num_sms);
     int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
-    tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<J.cta_count, tc::kThreads, smem, st>>>(one);
+    launch_k(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, J.cta_count, tc::kThreads, smem, st, one);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -684,8 +694,8 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     for (int i = 0; i < nj; ++i) jobs.j[i].rows_per_cta = per;
     dim3 grid(ctas, nj);
     int smem = tc::kDwStages * max_stage + 256 + 1024;
-    if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kDwThreads, smem, st>>>(jobs);
-    else tc::k_tc_dw<64><<<grid, tc::kDwThreads, smem, st>>>(jobs);
+    if (n_tile == 256) launch_k(tc::k_tc_dw<256>, grid, tc::kDwThreads, smem, st, jobs);
+    else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -695,10 +705,10 @@ static int thin_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   int l = B.n - 1;
   int width = B.L[l].k_in, out = B.L[l].k_out;
   int blocks = std::min((rows + 31) / 32, h->bf16->num_sms * 8);
-  if (out == 3 && width == 256) k_thin_fwd<3, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
-  else if (out == 3 && width == 512) k_thin_fwd<3, 2><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
-  else if (out == 1 && width == 256) k_thin_fwd<1, 1><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
-  else if (out == 1 && width == 512) k_thin_fwd<1, 2><<<blocks, 256, 0, st>>>(rows, B.act[l], B.ld[l], W, bias, B.logits);
+  if (out == 3 && width == 256) launch_k(k_thin_fwd<3, 1>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 3 && width == 512) launch_k(k_thin_fwd<3, 2>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 1 && width == 256) launch_k(k_thin_fwd<1, 1>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
+  else if (out == 1 && width == 512) launch_k(k_thin_fwd<1, 2>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
   else return fail(h, MARF_ERR_UNSUPPORTED, "bf16: output layer must be 3- or 1-wide over 256/512 features");
   BF_LAUNCH(h);
   return MARF_OK;
@@ -718,13 +728,13 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   int dxthreads = 256 / per_row * per_row;             // threads per block: multiple of per_row
   int dxblocks = std::min((rows * per_row + dxthreads - 1) / dxthreads, S->num_sms * 16);
   if (out == 3) {
-    k_thin_dw<3><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+    launch_k(k_thin_dw<3>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<3><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
+    launch_k(k_thin_dx<3>, dxblocks, dxthreads, 0, st, rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   } else {
-    k_thin_dw<1><<<nblk, blk, smem, st>>>(rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+    launch_k(k_thin_dw<1>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
     BF_LAUNCH(h);
-    k_thin_dx<1><<<dxblocks, dxthreads, 0, st>>>(rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
+    launch_k(k_thin_dx<1>, dxblocks, dxthreads, 0, st, rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   }
   BF_LAUNCH(h);
   return MARF_OK;
@@ -758,7 +768,7 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
     }
   }
   dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
-  k_pack_table<<<grid, 256, 0, st>>>(t);
+  launch_k(k_pack_table, grid, 256, 0, st, t);
   BF_LAUNCH(h);
   return MARF_OK;
 }
@@ -784,7 +794,7 @@ static int unpack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
     }
   }
   dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
-  k_unpack_table<<<grid, 256, 0, st>>>(t);
+  launch_k(k_unpack_table, grid, 256, 0, st, t);
   BF_LAUNCH(h);
   return MARF_OK;
 }
@@ -805,14 +815,14 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
   bool implicit = c.mask_mode == MARF_MASK_IMPLICIT;
   {
     dim3 eg((rg.padded + 127) / 128);
-    if (h->geo.L == 8) k_encode_bf16<8><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
-    else if (h->geo.L == 10) k_encode_bf16<10><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
-    else if (h->geo.L == 4) k_encode_bf16<4><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
-    else k_encode_bf16<0><<<eg, 128, 0, st>>>(h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    if (h->geo.L == 8) launch_k(k_encode_bf16<8>, eg, 128, 0, st, h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else if (h->geo.L == 10) launch_k(k_encode_bf16<10>, eg, 128, 0, st, h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else if (h->geo.L == 4) launch_k(k_encode_bf16<4>, eg, 128, 0, st, h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
+    else launch_k(k_encode_bf16<0>, eg, 128, 0, st, h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
   }
   BF_LAUNCH(h);
   if (implicit && !(h->feats_valid && h->n_chunks == 1)) {
-    k_mask_features_bf16<<<rg.padded, 128, 0, st>>>(h->geo, rg, io->rgb, io->embed, c.mask_embed_dim, c.mask_uv_freqs,
+    launch_k(k_mask_features_bf16, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, c.mask_embed_dim, c.mask_uv_freqs,
                                                     S->msk.act[0], S->msk.ld[0]);
     BF_LAUNCH(h);
     h->feats_valid = h->n_chunks == 1;
@@ -838,7 +848,7 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-    k_loss_stats<<<std::min((rg.padded + 255) / 256, 592), 256, 0, st>>>(h->geo, rg, a, io->loss_sums);
+    launch_k(k_loss_stats, std::min((rg.padded + 255) / 256, 592), 256, 0, st, h->geo, rg, a, io->loss_sums);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -859,7 +869,7 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.edge_label = io->edges; ga.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   ga.dlogits = S->img.dlogits; ga.dld = 4;
   ga.dmlogits = implicit ? S->msk.dlogits : nullptr; ga.dmld = 4;
-  k_loss_grad<<<(rg.padded + 127) / 128, 128, 0, st>>>(h->geo, rg, ga, h->coef);
+  launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
   BF_LAUNCH(h);
   BfChain* c_img[1] = {&S->img};
   BfChain* c_msk[1] = {&S->msk};
@@ -867,7 +877,7 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   if (rc) return rc;
   rc = launch_dx_all(h, st, c_img, 1, rg.padded);
   if (rc) return rc;
-  k_encode_backward<<<(rg.padded + 255) / 256, 256, 0, st>>>(h->geo, rg, h->Hm, S->dX0, 64, h->G);
+  launch_k(k_encode_backward, (rg.padded + 255) / 256, 256, 0, st, h->geo, rg, h->Hm, S->dX0, 64, h->G);
   BF_LAUNCH(h);
   if (implicit) {
     rc = thin_bwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
@@ -908,7 +918,7 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const marf_config& c = h->cfg;
   int rc = engine_begin_backward(h, io, st);
   if (rc) return rc;
-  k_loss_coef<<<1, 1, 0, st>>>(io->loss_sums, io->norm_rgb, io->norm_edge, c.use_edges, h->coef);
+  launch_k(k_loss_coef, 1, 1, 0, st, io->loss_sums, io->norm_rgb, io->norm_edge, c.use_edges, h->coef);
   BF_LAUNCH(h);
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     if (!h->acts_valid) {
@@ -962,7 +972,7 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     bf16* d = nullptr;
     if (cudaMalloc(&d, (size_t)r * c * 2) != cudaSuccess) return nullptr;
     int tot = r * c;
-    k_pack_bf16<<<(tot + 255) / 256, 256, 0, st>>>(src, r, c, d, r, c, 0);
+    launch_k(k_pack_bf16, (tot + 255) / 256, 256, 0, st, src, r, c, d, r, c, 0);
     return d;
   };
   int rc = MARF_OK;
@@ -998,7 +1008,7 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
       p.out_f32 = out; p.ld_out = 64; p.n_store = 64;
       int smem = tc::gemm_smem(64, p.k_chunks, false).total + 1024;
       fill(tA, tW, tA);
-      if (!rc) tc::k_tc_gemm<64, tc::EPI_PLAIN_F32><<<grid, tc::kThreads, smem, st>>>(jobs);
+      if (!rc) launch_k(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, grid, tc::kThreads, smem, st, jobs);
     } else {
       if (cudaMalloc(&dOut, (size_t)rows * N * 2) != cudaSuccess) return MARF_ERR_CUDA;
       if (!rc) rc = make_tmap(&tmp, &S, &tO, dOut, rows, N, 128);
@@ -1014,20 +1024,20 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
         p.bias = aux;
         fill(tA, tW, tO);
         if (!rc) {
-          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
-          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_BIAS_RELU><<<grid, tc::kThreads, smem, st>>>(jobs);
+          if (n_tile == 256) launch_k(tc::k_tc_gemm<256, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
+          else if (n_tile == 128) launch_k(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
           else rc = MARF_ERR_INVALID;
         }
       } else {
         uint32_t* dBits = nullptr;
         if (cudaMalloc(&dBits, (size_t)rows * (N / 32) * 4) != cudaSuccess) return MARF_ERR_CUDA;
-        k_make_bits<<<(rows * (N / 32) + 255) / 256, 256, 0, st>>>(rows, N, aux, dBits);
+        launch_k(k_make_bits, (rows * (N / 32) + 255) / 256, 256, 0, st, rows, N, aux, dBits);
         p.bits_in = dBits;
         p.bits_ld = N / 32;
         fill(tA, tW, tO);
         if (!rc) {
-          if (n_tile == 256) tc::k_tc_gemm<256, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
-          else if (n_tile == 128) tc::k_tc_gemm<128, tc::EPI_RELU_MASK><<<grid, tc::kThreads, smem, st>>>(jobs);
+          if (n_tile == 256) launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, grid, tc::kThreads, smem, st, jobs);
+          else if (n_tile == 128) launch_k(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, grid, tc::kThreads, smem, st, jobs);
           else rc = MARF_ERR_INVALID;
         }
         cudaStreamSynchronize(st);
@@ -1035,7 +1045,7 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
       }
       if (!rc) {
         long long tot = (long long)rows * N;
-        k_bf16_to_f32<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(tot, dOut, out);
+        launch_k(k_bf16_to_f32, (unsigned)((tot + 255) / 256), 256, 0, st, tot, dOut, out);
       }
       if (dTrace) {
         cudaStreamSynchronize(st);
@@ -1076,8 +1086,8 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     int smem = tc::kDwStages * stage + 256 + 1024;
     dim3 grid(ctas, n_tiles_n);
     if (!rc) {
-      if (n_tile == 256) tc::k_tc_dw<256><<<grid, tc::kDwThreads, smem, st>>>(jobs);
-      else tc::k_tc_dw<64><<<grid, tc::kDwThreads, smem, st>>>(jobs);
+      if (n_tile == 256) launch_k(tc::k_tc_dw<256>, grid, tc::kDwThreads, smem, st, jobs);
+      else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
     }
   } else {
     return MARF_ERR_INVALID;

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,10 @@ __device__ __forceinline__ void apply_h(const float* __restrict__ Hm, float x, f
   v = __fdiv_rn(q1, qz);
 }
 
+// Programmatic dependent launch: block until every kernel this launch depends on has completed and flushed.
+// A no-op for launches without the programmatic-stream-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -58,6 +63,28 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Every kernel of the step is launched with programmatic stream serialization (PDL): the next kernel's launch and
+// prologue overlap the previous kernel's tail; each kernel calls griddepcontrol.wait before it touches dependent data.
+// MARF_NO_PDL=1 falls back to plain stream-ordered launches.
+inline bool use_pdl() {
+  static const bool on = getenv("MARF_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }

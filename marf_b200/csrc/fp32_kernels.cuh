@@ -100,6 +100,7 @@ __device__ void expm_coop(double* X /*[N*N] in: A, scratch*/, double* T, double*
 
 // one block (64 threads) per patch
 static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float* __restrict__ out9) {
+  pdl_wait();
   __shared__ double X[9], T[9], R[9];
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) {
@@ -114,6 +115,7 @@ static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float
 // G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches); one block per patch
 static __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
                                int n_local, float* __restrict__ g_warp) {
+  pdl_wait();
   __shared__ double X[36], T[36], R[36];
   const int bl = blockIdx.x, tid = threadIdx.x;
   const int b = bl + patch_offset;
@@ -148,6 +150,7 @@ static __global__ void k_sl3_backward(const float* __restrict__ warp, const doub
 
 // warped crop corners (warp.py:83-93): [(X0,Y0),(X0,Y1),(X1,Y1),(X1,Y0)]
 static __global__ void k_warp_corners(Geo g, const float* __restrict__ Hm, int n, float* __restrict__ out) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * 4) return;
   int b = i / 4, c = i % 4;
@@ -187,6 +190,7 @@ __device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int
 
 static __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [batch_global,9] or identity */,
                          int identity, float* __restrict__ X0, int ld) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
   float* o = X0 + (size_t)t * ld;
@@ -219,6 +223,7 @@ static __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm 
 // backward of the prologue: dX0 [n,ld] -> per-patch G = sum_p dq (x) [x,y,1]  (SURVEY.md §8 a-4,a-5)
 static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ Hm, const float* __restrict__ dX0,
                                   int ld, double* __restrict__ G /* [batch,9] local patches */) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = t < rg.count;
   int b = -1, r = 0, c = 0;
@@ -292,6 +297,7 @@ static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restr
 // ============================================================================================
 static __global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
                                 int embed_dim, int n_freqs, float* __restrict__ F, int ld) {
+  pdl_wait();
   int t = blockIdx.x;
   float* o = F + (size_t)t * ld;
   if (t >= rg.count) {
@@ -372,6 +378,7 @@ static __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const
                                                const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                const float* __restrict__ aux, int ldaux, int k_split) {
   constexpr int BN = 16 * TN;
+  pdl_wait();
   __shared__ __align__(16) float As[2][GBK][GBM];
   __shared__ __align__(16) float Bs[2][GBK][GBM];   // only the first BN columns are used
   const int tid = threadIdx.x;
@@ -444,6 +451,7 @@ static __global__ void __launch_bounds__(256) k_sgemm(int M, int N, int K, const
 
 // db[j] += sum_m dY[m,j]
 static __global__ void k_colsum(int M, int N, const float* __restrict__ dY, int ld, float* __restrict__ db, int rows_per_block) {
+  pdl_wait();
   __shared__ float red[8][33];
   int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int n = blockIdx.x * 32 + tx;
@@ -463,12 +471,14 @@ static __global__ void k_colsum(int M, int N, const float* __restrict__ dY, int 
 
 // weight (un)packing between torch layouts and the padded workspace
 static __global__ void k_pack(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp, int prow, int pcol) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= prow * pcol) return;
   int r = i / pcol, c = i - r * pcol;
   Wp[i] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f;
 }
 static __global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* __restrict__ W, int rows, int cols) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   int r = i / cols, c = i - r * cols;
@@ -477,6 +487,7 @@ static __global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* _
 // copy `cols` columns between row-major buffers (skip-connection concat / split)
 static __global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int lds, int soff, float* __restrict__ dst,
                             int ldd, int doff, int accumulate) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * cols) return;
   int m = (int)(i / cols), c = (int)(i - (long long)m * cols);
@@ -487,6 +498,7 @@ static __global__ void k_copy_cols(int M, int cols, const float* __restrict__ sr
 // dY_prev[m,j] = dX[m,j] * (act[m,j] > 0) for j < cols
 static __global__ void k_relu_mask(int M, int cols, const float* __restrict__ dX, int ldx, const float* __restrict__ act,
                             int lda, float* __restrict__ dY, int ldy) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * cols) return;
   int m = (int)(i / cols), c = (int)(i - (long long)m * cols);
@@ -521,6 +533,7 @@ __device__ __forceinline__ void block_sum_atomic(double v, double* dst, double* 
 }
 
 static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __restrict__ sums) {
+  pdl_wait();
   __shared__ double red[32];
   double s_rgb = 0, n_rgb = 0, s_mask = 0, n_mask = 0, bad = 0;
   const long long per = (long long)g.rows * g.w;
@@ -559,6 +572,7 @@ static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __res
 
 // static mask sum (disk masks): N_RGB = 3 * sum m over the local shard
 static __global__ void k_sum_f32(const float* __restrict__ x, long long n, double scale, double* __restrict__ out) {
+  pdl_wait();
   double s = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s += (double)x[i];
@@ -576,6 +590,7 @@ struct EdgeArgs {
   const float* mask_pred;      // implicit mode [n_total]
 };
 static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __restrict__ sums) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   double s = 0, nn = 0;
   if (i < n_total) {
@@ -599,6 +614,7 @@ static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double
 // resolve normalisers on device (after an optional all-reduce of `sums`): no host round trip
 static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
                             int use_edges, LossCoef* __restrict__ out) {
+  pdl_wait();
   double n_rgb = norm_rgb_host > 0 ? norm_rgb_host : sums[MARF_N_RGB];
   double n_edge = norm_edge_host > 0 ? norm_edge_host : sums[MARF_N_EDGE];
   LossCoef c;
@@ -621,6 +637,7 @@ struct GradArgs {
 };
 
 static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
   float* dl = a.dlogits + (size_t)t * a.dld;
@@ -668,6 +685,7 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
 
 // plain sigmoid of the first 3 columns (render path)
 static __global__ void k_sigmoid_out(int n, const float* __restrict__ logits, int ld, float* __restrict__ out) {
+  pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
 #pragma unroll
@@ -686,6 +704,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int rows, int w, int interleaved,
                             double* __restrict__ mag /* planar [n,ch,rows,w] */) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)n * ch * rows * w;
   if (i >= total) return;
@@ -712,6 +731,7 @@ static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch,
 }
 
 static __global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)planes * rows * w;
   if (i >= total) return;

@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     mbar_init(w_full, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     fence_barrier_init();
+    // the weights were packed at least two launches ago: fetch them while the previous kernel is still draining
+    mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
+    for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &J.tmW, c * kChunkK, n0, w_full);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   if (EPI == EPI_BIAS_RELU && warp >= 2)
@@ -133,12 +136,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernel's output
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
-      for (int c = 0; c < p.k_chunks; ++c) tma_load_2d(sW + c * N_TILE * 128, &J.tmW, c * kChunkK, n0, w_full);
       uint32_t it = 0;
       const int kAhead = p.prefetch_ahead;           // tiles prefetched into L2 ahead of the SMEM ring (0: off)
       if (!J.flags_in && kAhead > 0)
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL
 
   if (n_iter > 0) {
     if (warp == 0) {
