@@ -447,6 +447,7 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   // the mask head's last-layer gradient is staged in its own logits buffer's twin: reuse dYb tail is unsafe,
   // so it is written after the image chain has consumed dYa (two launches of the same kernel).
   ga.dmlogits = nullptr; ga.dmld = 0;
+  ga.dl_bf16 = nullptr; ga.dml_bf16 = nullptr;
   launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
   LAUNCH_CHECK(h);
   float* dx0 = nullptr;

@@ -336,6 +336,8 @@ struct BfChain {
   uint32_t* flags_bwd[MARF_MAX_LAYERS] = {};       // flags_bwd[l]: per-tile completion counters of dY[l] (written by dX of layer l+1)
   float* logits = nullptr;                // [chunk,4] fp32
   float* dlogits = nullptr;               // [chunk,4] fp32
+  bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW
+  CUtensorMap tmDL64;
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
 };
@@ -423,8 +425,9 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
   }
   B.logits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
   B.dlogits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
-  if (!B.logits || !B.dlogits) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (logits)");
-  return MARF_OK;
+  B.dl16 = (bf16*)ws_alloc(h, (size_t)h->chunk * 64 * 2);
+  if (!B.logits || !B.dlogits || !B.dl16) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (logits)");
+  return make_tmap(h, S, &B.tmDL64, B.dl16, h->chunk, 64, 64);
 }
 
 static int set_tc_attrs(marf_handle* h) {
@@ -663,6 +666,24 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     for (int ci = 0; ci < n_chains; ++ci) {
       BfChain& B = *chains[ci];
       Chain& F = *B.f32;
+      if (pass == 0 && B.L[B.n - 1].k_in == 256) {
+        // output layer (3-/1-wide): dW = dlogits^T X_last through the same kernel (dlogits as a zero-padded bf16 tile)
+        if (nj >= tc::kDwMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
+        const int l = B.n - 1;
+        tc::DwJob& J = jobs.j[nj++];
+        J.tmDY = B.tmDL64;
+        J.tmX = B.tmAct64[l];
+        J.rows = rows;
+        J.m_halves = 1;
+        J.m_valid = B.L[l].k_out;
+        J.n_valid = B.L[l].k_in;
+        J.n0 = 0;
+        J.ld_w = F.ld_in[l];
+        J.do_bias = 1;
+        J.dW = F.gWp[l];
+        J.db = F.gbp[l];
+        max_stage = std::max(max_stage, (2 + 256 / 64) * tc::kDwSlab);
+      }
       for (int l = 0; l < B.n - 1; ++l) {
         BfLayer& L = B.L[l];
         const int lt = L.kp >= 256 ? 256 : 64;
@@ -727,13 +748,18 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   int per_row = width / 8;
   int dxthreads = 256 / per_row * per_row;             // threads per block: multiple of per_row
   int dxblocks = std::min((rows * per_row + dxthreads - 1) / dxthreads, S->num_sms * 16);
+  const bool tc_dw = width == 256;           // then launch_dw_all carries the output layer's dW/db as a tensor-core job
   if (out == 3) {
-    launch_k(k_thin_dw<3>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
-    BF_LAUNCH(h);
+    if (!tc_dw) {
+      launch_k(k_thin_dw<3>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+      BF_LAUNCH(h);
+    }
     launch_k(k_thin_dx<3>, dxblocks, dxthreads, 0, st, rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   } else {
-    launch_k(k_thin_dw<1>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
-    BF_LAUNCH(h);
+    if (!tc_dw) {
+      launch_k(k_thin_dw<1>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
+      BF_LAUNCH(h);
+    }
     launch_k(k_thin_dx<1>, dxblocks, dxthreads, 0, st, rows, width, B.dlogits, W, B.bits[l], B.ld[l] / 32, B.dY[l - 1], B.L[l - 1].np);
   }
   BF_LAUNCH(h);
@@ -869,6 +895,8 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.edge_label = io->edges; ga.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   ga.dlogits = S->img.dlogits; ga.dld = 4;
   ga.dmlogits = implicit ? S->msk.dlogits : nullptr; ga.dmld = 4;
+  ga.dl_bf16 = S->img.dl16;
+  ga.dml_bf16 = implicit ? S->msk.dl16 : nullptr;
   launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
   BF_LAUNCH(h);
   BfChain* c_img[1] = {&S->img};

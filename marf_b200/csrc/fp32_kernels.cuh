@@ -634,6 +634,8 @@ struct GradArgs {
   int label_channels;
   float* dlogits; int dld;     // out [n_pad, dld]
   float* dmlogits; int dmld;   // out [n_pad, dmld] (implicit only)
+  __nv_bfloat16* dl_bf16;      // optional bf16 copies [n_pad, 64] (zero padded) for the tensor-core dW of the output layers
+  __nv_bfloat16* dml_bf16;
 };
 
 static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
@@ -642,9 +644,15 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
   if (t >= rg.padded) return;
   float* dl = a.dlogits + (size_t)t * a.dld;
   float* dm = a.dmlogits ? a.dmlogits + (size_t)t * a.dmld : nullptr;
+  uint4* dlb = a.dl_bf16 ? reinterpret_cast<uint4*>(a.dl_bf16 + (size_t)t * 64) : nullptr;
+  uint4* dmb = a.dml_bf16 ? reinterpret_cast<uint4*>(a.dml_bf16 + (size_t)t * 64) : nullptr;
+  if (dlb) for (int j = 1; j < 8; ++j) dlb[j] = make_uint4(0u, 0u, 0u, 0u);
+  if (dmb) for (int j = 1; j < 8; ++j) dmb[j] = make_uint4(0u, 0u, 0u, 0u);
   if (t >= rg.count) {
     for (int j = 0; j < a.dld; ++j) dl[j] = 0.f;
     if (dm) for (int j = 0; j < a.dmld; ++j) dm[j] = 0.f;
+    if (dlb) dlb[0] = make_uint4(0u, 0u, 0u, 0u);
+    if (dmb) dmb[0] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
   const LossCoef cf = *coefp;
@@ -664,6 +672,10 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
     dl[c] = k_rgb * d * m * m * p * (1.f - p);
   }
   for (int j = 3; j < a.dld; ++j) dl[j] = 0.f;
+  if (dlb) {
+    __nv_bfloat162 p01 = __floats2bfloat162_rn(dl[0], dl[1]), p2 = __floats2bfloat162_rn(dl[2], 0.f);
+    dlb[0] = make_uint4(*reinterpret_cast<uint32_t*>(&p01), *reinterpret_cast<uint32_t*>(&p2), 0u, 0u);
+  }
   if (dm) {
     // d all / d m_p  
     double gm = (double)a.c_rgb * (2.0 * m * sum_d2 * cf.inv_n_rgb - cf.s_over_n2)
@@ -680,6 +692,10 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
     }
     dm[0] = (float)(gm * (double)(m * (1.f - m)));
     for (int j = 1; j < a.dmld; ++j) dm[j] = 0.f;
+    if (dmb) {
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(dm[0], 0.f);
+      dmb[0] = make_uint4(*reinterpret_cast<uint32_t*>(&p0), 0u, 0u, 0u);
+    }
   }
 }
 

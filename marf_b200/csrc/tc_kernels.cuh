@@ -343,7 +343,7 @@ struct DwJob {
   float* dW;            // [out, ld_w] fp32, accumulated with red.add
   float* db;            // [out] fp32
 };
-constexpr int kDwMaxJobs = 8;
+constexpr int kDwMaxJobs = 12;
 struct DwJobs { DwJob j[kDwMaxJobs]; };
 
 constexpr int kDwStages = 3;
