@@ -425,7 +425,7 @@ static int edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   e.edge_pred = ep; e.edge_label = io->edges; e.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   e.masks_eroded = io->masks_eroded;
   e.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-  launch_k(k_edge_stats, (unsigned)((h->n_local + 255) / 256), 256, 0, st, h->geo, h->n_local, e, io->loss_sums);
+  launch_k(k_edge_stats, (unsigned)std::min<long long>((h->n_local + 255) / 256, 592), 256, 0, st, h->geo, h->n_local, e, io->loss_sums);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }

@@ -24,6 +24,10 @@ using bf16 = __nv_bfloat16;
   do {                                                                                          \
     (h)->launches++;                                                                            \
     cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ == cudaSuccess && getenv("MARF_DEBUG_SYNC")) {                                      \
+      e__ = cudaDeviceSynchronize();                                                            \
+      if (e__ != cudaSuccess) fprintf(stderr, "MARF_DEBUG_SYNC: fault after launch at %s:%d\n", __FILE__, __LINE__); \
+    }                                                                                           \
     if (e__ != cudaSuccess) return fail(h, MARF_ERR_CUDA, std::string("bf16 kernel launch: ") + cudaGetErrorString(e__)); \
   } while (0)
 
@@ -98,6 +102,105 @@ __global__ void k_mask_features_bf16(Geo g, PxRange rg, const float* __restrict_
     o[k_col + j] = __float2bfloat16(val);
   }
   for (int j = k_col + k_uv + threadIdx.x; j < ld; j += blockDim.x) o[j] = __float2bfloat16(0.f);
+}
+
+// ---- mask head layer 0 through the colour-class table (model/planar.py:342-349).  trunc(rgb) of a [0,1] image is 0 or 1,
+// so the 384-wide colour embedding takes one of 8 values per pixel: layer 0 = T[class] + W0[:,384:] . PosEmbedding(xy),
+// with T[c] = b0 + W0[:, :384] . colE(c) rebuilt every step (8 x 256 entries) — algebraically identical to the dense layer.
+// Feature row (64 bf16): [PosEmbedding(xy) (2+4F) | onehot(class) (8) | onehot(class) (8) | 0...].  The two one-hot groups
+// multiply the hi and lo bf16 halves of the class table T that k_mask_table writes into the packed layer-0 weights, so
+// the colour part needs no epilogue work, and in the dW GEMM the first one-hot group yields the per-class column sums.
+__global__ void k_mask_uv_cls(Geo g, PxRange rg, const float* __restrict__ rgb, int n_freqs, bf16* __restrict__ UV,
+                              int* __restrict__ bad) {
+  pdl_wait();
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= rg.padded) return;
+  uint4* o = reinterpret_cast<uint4*>(UV + (size_t)t * 64);
+  float f[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) f[j] = 0.f;
+  unsigned char cl = 0;
+  if (t < rg.count) {
+    int b, r, c;
+    long long i = rg.first + t;
+    decode_px(g, i, b, r, c);
+    long long per = (long long)g.rows * g.w;
+    long long rem = i - (long long)b * per;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      long long idx = (long long)rgb[((long long)b * 3 + ch) * per + rem];
+      if (idx < 0 || idx > 1) atomicOr(bad, 1);
+      cl |= (unsigned char)((idx & 1) << ch);
+    }
+    float x, y;
+    grid_xy(g, r, c, x, y);
+    f[0] = x; f[1] = y;
+#pragma unroll
+    for (int fi = 0; fi < 15; ++fi) {
+      if (fi < n_freqs) {
+        const float fr = (float)(1 << fi);
+        f[2 + 4 * fi + 0] = sinf(fr * x); f[2 + 4 * fi + 1] = sinf(fr * y);
+        f[2 + 4 * fi + 2] = cosf(fr * x); f[2 + 4 * fi + 3] = cosf(fr * y);
+      }
+    }
+  }
+  if (t < rg.count) {
+    const int k_uv = 2 + 4 * n_freqs;
+#pragma unroll
+    for (int j = 0; j < 64; ++j)
+      if (j == k_uv + cl || j == k_uv + 8 + cl) f[j] = 1.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    o[j] = make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                      tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+}
+
+// T[c][j] = b0[j] + sum_ch sum_e W0[j][ch*E + e] * embed[bit_ch(c)][e], one warp per (class, output) pair, written as
+// bf16 hi / lo halves into columns k_uv + c and k_uv + 8 + c of the packed forward weights Wk [256, 64] of layer 0
+__global__ void k_mask_table(const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ embed,
+                             int k_in, int k_out, int edim, int k_uv, bf16* __restrict__ Wk, int ldk) {
+  pdl_wait();
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= 8 * k_out) return;
+  const int c = gw / k_out, j = gw - c * k_out;
+  const float* w = W0 + (size_t)j * k_in;
+  float acc = 0.f;
+  for (int i = lane; i < 3 * edim; i += 32) acc = fmaf(w[i], embed[(size_t)((c >> (i / edim)) & 1) * edim + (i % edim)], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float t = acc + b0[j];
+    const bf16 hi = __float2bfloat16(t);
+    Wk[(size_t)j * ldk + k_uv + c] = hi;
+    Wk[(size_t)j * ldk + k_uv + 8 + c] = __float2bfloat16(t - __bfloat162float(hi));
+  }
+}
+
+// Layer-0 gradient of the mask head from the dW tile X = dY0^T [uv | onehot | onehot] ([k_out, 64] fp32):
+//   uv columns          -> dW0[:, 3E : 3E + k_uv]
+//   S[c][j] = X[j][k_uv + c] (per-class column sums of dY0)
+//   dW0[j][ch*E + e] = sum_c S[c][j] * embed[bit_ch(c)][e],   db0[j] = sum_c S[c][j]
+__global__ void k_mask_dw_finalize(const float* __restrict__ X, const float* __restrict__ embed, int edim, int k_out, int k_uv,
+                                   float* __restrict__ gW0, int ldw, float* __restrict__ gb0) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncol = 3 * edim + k_uv;
+  if (i >= k_out * ncol) return;
+  const int j = i / ncol, col = i - j * ncol;
+  const float* x = X + (size_t)j * 64;
+  if (col >= 3 * edim) {
+    gW0[(size_t)j * ldw + col] = x[col - 3 * edim];
+    return;
+  }
+  const int ch = col / edim, e = col - ch * edim;
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float v = x[k_uv + c];
+    if ((c >> ch) & 1) s1 += v; else s0 += v;
+  }
+  gW0[(size_t)j * ldw + col] = s0 * embed[e] + s1 * embed[edim + e];
+  if (col == 0) gb0[j] = s0 + s1;
 }
 
 // W fp32 [rows, cols] -> bf16 [prow, pcol] (zero padded), optionally transposed: out[c][r]
@@ -281,7 +384,7 @@ static __global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, f
 }
 
 // table-driven (un)packing: one launch for every layer of both networks
-struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed
+struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode, src_ld, col_off; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed
 constexpr int kMaxPack = 48;
 struct PackTable { PackEntry e[kMaxPack]; int n; };
 static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
@@ -291,7 +394,7 @@ static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
     int pr = i / E.pcol, pc = i - pr * E.pcol;
     int r = E.mode == 2 ? pc : pr, c = E.mode == 2 ? pr : pc;
-    float v = (r < E.rows && c < E.cols) ? E.src[(size_t)r * E.cols + c] : 0.f;
+    float v = (r < E.rows && c < E.cols) ? E.src[(size_t)r * E.src_ld + E.col_off + c] : 0.f;
     if (E.mode == 0) reinterpret_cast<float*>(E.dst)[i] = v;
     else reinterpret_cast<bf16*>(E.dst)[i] = __float2bfloat16(v);
   }
@@ -340,6 +443,10 @@ struct BfChain {
   CUtensorMap tmDL64;
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
+  int col_off0 = 0;                       // class-table mode: layer 0 uses columns [col_off0, col_off0 + k_in) of W0
+  float* dW0x = nullptr;                  // [256, 64] fp32: dY0^T [uv | onehot | onehot] (class-table mode)
+  float* zero_bias = nullptr;             // [256] zeros: the class table carries b0
+  int* bad = nullptr;                     // device flag: a colour index outside {0,1} was seen
 };
 
 struct Bf16State {
@@ -364,13 +471,22 @@ static int make_tmap(marf_handle* h, Bf16State* S, CUtensorMap* m, void* base, i
 
 static int round64(int a) { return (a + 63) / 64 * 64; }
 
-static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bool need_dx0) {
+static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bool need_dx0, int class_cols = 0) {
   B.n = F.n;
   B.f32 = &F;
   B.need_dx0 = need_dx0;
+  B.col_off0 = class_cols;
+  if (class_cols > 0) {
+    B.dW0x = (float*)ws_alloc(h, 256 * 64 * sizeof(float));
+    B.zero_bias = (float*)ws_alloc(h, 256 * sizeof(float));
+    B.bad = (int*)ws_alloc(h, sizeof(int));
+    if (!B.dW0x || !B.zero_bias || !B.bad) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (class table)");
+    if (F.k_out[0] != 256 || F.k_in[0] - class_cols + 16 > 64)
+      return fail(h, MARF_ERR_UNSUPPORTED, "bf16 mask head: layer 0 must be 256 wide with at most 48 positional inputs");
+  }
   for (int l = 0; l < F.n; ++l) {
     BfLayer& L = B.L[l];
-    L.k_in = F.k_in[l];
+    L.k_in = l == 0 ? F.k_in[l] - class_cols : F.k_in[l];
     L.k_out = F.k_out[l];
     L.thin = L.k_out <= 4;
     L.kp = round64(L.k_in);
@@ -463,7 +579,7 @@ int bf16_create(marf_handle* h) {
   int rc = build_bf_chain(h, S, S->img, h->img, true);
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
-    rc = build_bf_chain(h, S, S->msk, h->msk, false);
+    rc = build_bf_chain(h, S, S->msk, h->msk, false, 3 * h->cfg.mask_embed_dim);
     if (rc) return rc;
   }
   S->dX0 = (float*)ws_alloc(h, (size_t)h->chunk * 64 * sizeof(float));
@@ -506,6 +622,7 @@ static tc::GemmJob fwd_job(BfChain& B, int l, int rows, int n_tile, int n0) {
   J.p.n_tiles = rows / 128;
   J.p.k_chunks = L.kp / 64;
   J.p.bias = B.f32->bp[l];
+  if (l == 0 && B.col_off0 > 0) J.p.bias = B.zero_bias;     // b0 is part of the class table inside Wk
   J.p.bits_out = B.bits[l + 1];
   J.p.bits_ld = B.ld[l + 1] / 32;
   J.p.reverse = getenv("MARF_CHAIN") ? 0 : (l & 1);   // start where the previous launch just finished (still in L2)
@@ -656,11 +773,12 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 }
 
 // all dW / db of the tensor-core layers of the given chains: one launch per N-tile width
-static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
+static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, long long row_first) {
   Bf16State* S = h->bf16;
+  (void)row_first;
   for (int pass = 0; pass < 2; ++pass) {          // pass 0: N_TILE=256 jobs, pass 1: N_TILE=64 jobs
     const int n_tile = pass == 0 ? 256 : 64;
-    tc::DwJobs jobs;
+    tc::DwJobs jobs{};
     int nj = 0;
     int max_stage = 0;
     for (int ci = 0; ci < n_chains; ++ci) {
@@ -704,6 +822,11 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
           J.do_bias = t == 0;
           J.dW = F.gWp[l];
           J.db = F.gbp[l];
+          if (l == 0 && B.col_off0 > 0) {
+            // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
+            // k_mask_dw_finalize turns into dW0 / db0
+            J.dW = B.dW0x; J.ld_w = 64; J.n_valid = 64; J.do_bias = 0;
+          }
           max_stage = std::max(max_stage, (J.m_halves * 2 + n_tile / 64) * tc::kDwSlab);
         }
       }
@@ -772,9 +895,10 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
   PackTable t;
   t.n = 0;
   int max_tot = 0;
-  auto add = [&](const float* src, void* dst, int rows, int cols, int prow, int pcol, int mode) {
+  auto add = [&](const float* src, void* dst, int rows, int cols, int prow, int pcol, int mode, int src_ld = -1, int col_off = 0) {
     PackEntry& e = t.e[t.n++];
     e.src = src; e.dst = dst; e.rows = rows; e.cols = cols; e.prow = prow; e.pcol = pcol; e.mode = mode;
+    e.src_ld = src_ld < 0 ? cols : src_ld; e.col_off = col_off;
     max_tot = std::max(max_tot, prow * pcol);
   };
   BfChain* chains[2] = {&S->img, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? &S->msk : nullptr};
@@ -789,8 +913,10 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
       if (t.n + 3 > kMaxPack) return fail(h, MARF_ERR_UNSUPPORTED, "too many layers");
       add(bs[ci][l], F.bp[l], 1, F.k_out[l], 1, F.ld_out[l], 0);
       if (B.L[l].thin) continue;
-      add(Ws[ci][l], B.L[l].Wk, B.L[l].k_out, B.L[l].k_in, B.L[l].np, B.L[l].kp, 1);
-      add(Ws[ci][l], B.L[l].Wt, B.L[l].k_out, B.L[l].k_in, B.L[l].kp, B.L[l].np, 2);
+      // (layer 0 of the mask head only multiplies the uv columns: a window of the caller's [k_out, k_in] matrix)
+      const int off = l == 0 ? B.col_off0 : 0;
+      add(Ws[ci][l], B.L[l].Wk, B.L[l].k_out, B.L[l].k_in, B.L[l].np, B.L[l].kp, 1, F.k_in[l], off);
+      add(Ws[ci][l], B.L[l].Wt, B.L[l].k_out, B.L[l].k_in, B.L[l].kp, B.L[l].np, 2, F.k_in[l], off);
     }
   }
   dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
@@ -847,11 +973,22 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
     else launch_k(k_encode_bf16<0>, eg, 128, 0, st, h->geo, rg, h->Hm, S->img.act[0], S->img.ld[0]);
   }
   BF_LAUNCH(h);
-  if (implicit && !(h->feats_valid && h->n_chunks == 1)) {
-    launch_k(k_mask_features_bf16, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, c.mask_embed_dim, c.mask_uv_freqs,
-                                                    S->msk.act[0], S->msk.ld[0]);
+  if (implicit) {
+    if (!(h->feats_valid && h->n_chunks == 1)) {
+      launch_k(k_mask_uv_cls, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, io->rgb, c.mask_uv_freqs, S->msk.act[0], S->msk.bad);
+      BF_LAUNCH(h);
+      if (h->n_chunks == 1) {
+        // once per data version: the class table needs trunc(rgb) in {0,1} (true for [0,1] images; checked, not assumed)
+        int bad = 0;
+        BF_TRY(h, cudaMemcpyAsync(&bad, S->msk.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+        BF_TRY(h, cudaStreamSynchronize(st));
+        if (bad) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 mask head: colour indices outside {0,1} (images must lie in [0,2))");
+      }
+      h->feats_valid = h->n_chunks == 1;
+    }
+    launch_k(k_mask_table, (8 * h->msk.k_out[0] * 32 + 255) / 256, 256, 0, st, io->mask_w[0], io->mask_b[0], io->embed,
+             h->msk.k_in[0], h->msk.k_out[0], c.mask_embed_dim, S->msk.L[0].k_in, S->msk.L[0].Wk, S->msk.L[0].kp);
     BF_LAUNCH(h);
-    h->feats_valid = h->n_chunks == 1;
   }
   // chain after chain, each followed at once by its output layer: the last hidden activation is still in L2
   BfChain* c_img[1] = {&S->img};
@@ -914,7 +1051,7 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
     if (rc) return rc;
   }
   BfChain* chains[2] = {&S->img, &S->msk};
-  return launch_dw_all(h, st, chains, implicit ? 2 : 1, rg.padded);
+  return launch_dw_all(h, st, chains, implicit ? 2 : 1, rg.padded, rg.first);
 }
 
 // shared with api.cu
@@ -948,6 +1085,8 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   if (rc) return rc;
   launch_k(k_loss_coef, 1, 1, 0, st, io->loss_sums, io->norm_rgb, io->norm_edge, c.use_edges, h->coef);
   BF_LAUNCH(h);
+  const bool implicit = c.mask_mode == MARF_MASK_IMPLICIT;
+  if (implicit) BF_TRY(h, cudaMemsetAsync(h->bf16->msk.dW0x, 0, 256 * 64 * sizeof(float), st));
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     if (!h->acts_valid) {
       rc = bf_forward_chunk(h, io, st, ci, false);
@@ -957,6 +1096,13 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
     if (rc) return rc;
   }
   h->acts_valid = false;
+  if (implicit) {
+    // colour columns of dW0 and db0 of the mask head from the per-class column sums of dY0 (all chunks)
+    const int tot = h->msk.k_out[0] * h->msk.k_in[0];
+    launch_k(k_mask_dw_finalize, (tot + 255) / 256, 256, 0, st, h->bf16->msk.dW0x, io->embed, c.mask_embed_dim, h->msk.k_out[0],
+             h->bf16->msk.L[0].k_in, h->msk.gWp[0], h->msk.ld_in[0], h->msk.gbp[0]);
+    BF_LAUNCH(h);
+  }
   rc = engine_finish_backward(h, io, st, false);
   if (rc) return rc;
   return unpack_all(h, st, io);
@@ -1104,7 +1250,7 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     ctas = (rows + per - 1) / per;
     // out holds [N, K] weights followed by [N] bias sums
     cudaMemsetAsync(out, 0, ((size_t)N * K + N) * sizeof(float), st);
-    tc::DwJobs jobs;
+    tc::DwJobs jobs{};
     for (int t = 0; t < n_tiles_n; ++t) {
       tc::DwJob& J = jobs.j[t];
       J.tmDY = tA; J.tmX = tM; J.rows = rows; J.rows_per_cta = per; J.m_halves = (N + 127) / 128; J.m_valid = N;

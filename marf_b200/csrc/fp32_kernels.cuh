@@ -591,10 +591,10 @@ struct EdgeArgs {
 };
 static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double* __restrict__ sums) {
   pdl_wait();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double red[32];
   double s = 0, nn = 0;
-  if (i < n_total) {
-    long long per = (long long)g.rows * g.w;
+  const long long per = (long long)g.rows * g.w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += (long long)gridDim.x * blockDim.x) {
     long long b = i / per, rem = i - b * per;
     double m = 1.0;
     if (a.mask_mode == MARF_MASK_DISK) m = (double)a.masks_eroded[i];
@@ -605,10 +605,10 @@ static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double
       double d = (a.edge_pred[(b * 3 + c) * per + rem] - l) * m;
       s += d * d;
     }
-    nn = 3.0 * m;
+    nn += 3.0 * m;
   }
-  s = warp_sum(s); nn = warp_sum(nn);
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[MARF_S_EDGE], s); atomicAdd(&sums[MARF_N_EDGE], nn); }
+  block_sum_atomic(s, &sums[MARF_S_EDGE], red);
+  block_sum_atomic(nn, &sums[MARF_N_EDGE], red);
 }
 
 // resolve normalisers on device (after an optional all-reduce of `sums`): no host round trip
@@ -646,8 +646,7 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
   float* dm = a.dmlogits ? a.dmlogits + (size_t)t * a.dmld : nullptr;
   uint4* dlb = a.dl_bf16 ? reinterpret_cast<uint4*>(a.dl_bf16 + (size_t)t * 64) : nullptr;
   uint4* dmb = a.dml_bf16 ? reinterpret_cast<uint4*>(a.dml_bf16 + (size_t)t * 64) : nullptr;
-  if (dlb) for (int j = 1; j < 8; ++j) dlb[j] = make_uint4(0u, 0u, 0u, 0u);
-  if (dmb) for (int j = 1; j < 8; ++j) dmb[j] = make_uint4(0u, 0u, 0u, 0u);
+  // (columns 8..63 of the bf16 copies are zero from allocation and never written)
   if (t >= rg.count) {
     for (int j = 0; j < a.dld; ++j) dl[j] = 0.f;
     if (dm) for (int j = 0; j < a.dmld; ++j) dm[j] = 0.f;
