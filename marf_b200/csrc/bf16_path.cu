@@ -234,7 +234,7 @@ __global__ void k_thin_fwd(int n, const bf16* __restrict__ X, int ld, const floa
   for (int o = 0; o < OUT; ++o) bo[o] = bias[o];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  constexpr int R = 4;                               // rows in flight per warp
+  constexpr int R = 8;                               // rows in flight per warp
   for (int row0 = warp * R; row0 < n; row0 += nwarps * R) {
     uint4 raw[R][KCH];
 #pragma unroll
@@ -439,8 +439,10 @@ struct BfChain {
   uint32_t* flags_bwd[MARF_MAX_LAYERS] = {};       // flags_bwd[l]: per-tile completion counters of dY[l] (written by dX of layer l+1)
   float* logits = nullptr;                // [chunk,4] fp32
   float* dlogits = nullptr;               // [chunk,4] fp32
-  bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW
-  CUtensorMap tmDL64;
+  bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW / dX
+  CUtensorMap tmDL64, tmDL128;
+  bf16* Wlast_t = nullptr;                // [k_in(last), 64] bf16: W_last^T zero padded (B operand of the output layer's dX GEMM)
+  CUtensorMap tmWlast_t;
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
   int col_off0 = 0;                       // class-table mode: layer 0 uses columns [col_off0, col_off0 + k_in) of W0
@@ -543,7 +545,17 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
   B.dlogits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
   B.dl16 = (bf16*)ws_alloc(h, (size_t)h->chunk * 64 * 2);
   if (!B.logits || !B.dlogits || !B.dl16) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (logits)");
-  return make_tmap(h, S, &B.tmDL64, B.dl16, h->chunk, 64, 64);
+  int rc = make_tmap(h, S, &B.tmDL64, B.dl16, h->chunk, 64, 64);
+  if (rc) return rc;
+  rc = make_tmap(h, S, &B.tmDL128, B.dl16, h->chunk, 64, 128);
+  if (rc) return rc;
+  const int kl = B.L[F.n - 1].k_in;
+  if (kl == 256) {
+    B.Wlast_t = (bf16*)ws_alloc(h, (size_t)kl * 64 * 2);
+    if (!B.Wlast_t) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (output layer)");
+    rc = make_tmap(h, S, &B.tmWlast_t, B.Wlast_t, kl, 64, 256);
+  }
+  return rc;
 }
 
 static int set_tc_attrs(marf_handle* h) {
@@ -553,6 +565,10 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
@@ -700,7 +716,7 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
 
 // dX of every tensor-core layer l >= 1 of the given chains in ONE launch (dY[l-1] = (dY[l] W_l) * relu_mask(act[l])),
 // chained through per-tile flags; then dX0 of the chains that need the gradient w.r.t. their input.
-static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
+static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, PxRange rg) {
   Bf16State* S = h->bf16;
   static const bool chain_mode = getenv("MARF_CHAIN") != nullptr;
   int max_depth = 0;
@@ -758,15 +774,21 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     J.tmOut = B.tmDY128[0];
     J.p.n_tiles = rows / 128;
     J.p.k_chunks = L.np / 64;
-    J.p.out_f32 = S->dX0;
-    J.p.ld_out = 64;
-    J.p.n_store = pad4(L.k_in);
     J.p.load_policy = tc::kEvictNormal;
     J.p.store_policy = tc::kEvictNormal;
+    J.p.geo = h->geo;
+    J.p.rg = rg;
+    J.p.Hm = h->Hm;
+    J.p.G = h->G;
+    J.p.wg_split = getenv("MARF_WG_SPLIT") ? 1 : 0;       // measured: one group doing both halves is faster
     J.cta_begin = 0;
     J.cta_count = std::min(J.p.n_tiles, S->num_sms);
     int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
-    launch_k(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, J.cta_count, tc::kThreads, smem, st, one);
+    // the epilogue is the backward of the encoding prologue: per-pixel (g_u, g_v) -> dq -> per-patch G
+    if (h->geo.L == 8) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 8>, J.cta_count, tc::kThreads, smem, st, one);
+    else if (h->geo.L == 10) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 10>, J.cta_count, tc::kThreads, smem, st, one);
+    else if (h->geo.L == 4) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, J.cta_count, tc::kThreads, smem, st, one);
+    else launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, J.cta_count, tc::kThreads, smem, st, one);
     BF_LAUNCH(h);
   }
   return MARF_OK;
@@ -848,7 +870,7 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 static int thin_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* W, const float* bias) {
   int l = B.n - 1;
   int width = B.L[l].k_in, out = B.L[l].k_out;
-  int blocks = std::min((rows + 31) / 32, h->bf16->num_sms * 8);
+  int blocks = std::min((rows + 63) / 64, h->bf16->num_sms * 8);
   if (out == 3 && width == 256) launch_k(k_thin_fwd<3, 1>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
   else if (out == 3 && width == 512) launch_k(k_thin_fwd<3, 2>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
   else if (out == 1 && width == 256) launch_k(k_thin_fwd<1, 1>, blocks, 256, 0, st, rows, B.act[l], B.ld[l], W, bias, B.logits);
@@ -872,6 +894,28 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
   int dxthreads = 256 / per_row * per_row;             // threads per block: multiple of per_row
   int dxblocks = std::min((rows * per_row + dxthreads - 1) / dxthreads, S->num_sms * 16);
   const bool tc_dw = width == 256;           // then launch_dw_all carries the output layer's dW/db as a tensor-core job
+  if (B.Wlast_t) {
+    // dY[n-2] = (dlogits W_last) * relu_mask: the same GEMM kernel as the hidden dX layers, K = 64 (3 or 1 real columns)
+    tc::GemmJobs one{};
+    one.n = 1;
+    tc::GemmJob& J = one.j[0];
+    J.tmA = B.tmDL128;
+    J.tmW = B.tmWlast_t;
+    J.tmOut = B.tmDY128[l - 1];
+    J.p.n_tiles = rows / 128;
+    J.p.k_chunks = 1;
+    J.p.bits_in = B.bits[l];
+    J.p.bits_ld = B.ld[l] / 32;
+    J.p.reverse = 0;
+    J.p.load_policy = tc::kEvictNormal;        // dlogits are read again by the dW pass
+    J.p.store_policy = tc::kEvictLast;
+    J.cta_begin = 0;
+    J.cta_count = std::min(J.p.n_tiles, S->num_sms);
+    int smem_g = tc::gemm_smem(256, 1, true).total + 1024;
+    launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, J.cta_count, tc::kThreads, smem_g, st, one);
+    BF_LAUNCH(h);
+    return MARF_OK;
+  }
   if (out == 3) {
     if (!tc_dw) {
       launch_k(k_thin_dw<3>, nblk, blk, smem, st, rows, width, B.dlogits, B.act[l], B.ld[l], F.gWp[l], F.ld_in[l], F.gbp[l], rpb);
@@ -912,6 +956,7 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
       if (!Ws[ci][l] || !bs[ci][l]) return fail(h, MARF_ERR_INVALID, "null layer parameter");
       if (t.n + 3 > kMaxPack) return fail(h, MARF_ERR_UNSUPPORTED, "too many layers");
       add(bs[ci][l], F.bp[l], 1, F.k_out[l], 1, F.ld_out[l], 0);
+      if (B.L[l].thin && B.Wlast_t) add(Ws[ci][l], B.Wlast_t, B.L[l].k_out, B.L[l].k_in, B.L[l].k_in, 64, 2);
       if (B.L[l].thin) continue;
       // (layer 0 of the mask head only multiplies the uv columns: a window of the caller's [k_out, k_in] matrix)
       const int off = l == 0 ? B.col_off0 : 0;
@@ -1040,14 +1085,12 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   BfChain* c_msk[1] = {&S->msk};
   int rc = thin_bwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
   if (rc) return rc;
-  rc = launch_dx_all(h, st, c_img, 1, rg.padded);
+  rc = launch_dx_all(h, st, c_img, 1, rg.padded, rg);       // ends with dX0 + encoding backward -> per-patch G
   if (rc) return rc;
-  launch_k(k_encode_backward, (rg.padded + 255) / 256, 256, 0, st, h->geo, rg, h->Hm, S->dX0, 64, h->G);
-  BF_LAUNCH(h);
   if (implicit) {
     rc = thin_bwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
     if (rc) return rc;
-    rc = launch_dx_all(h, st, c_msk, 1, rg.padded);
+    rc = launch_dx_all(h, st, c_msk, 1, rg.padded, rg);
     if (rc) return rc;
   }
   BfChain* chains[2] = {&S->img, &S->msk};

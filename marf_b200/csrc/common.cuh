@@ -48,6 +48,20 @@ __device__ __forceinline__ void apply_h(const float* __restrict__ Hm, float x, f
   v = __fdiv_rn(q1, qz);
 }
 
+struct PxRange {
+  long long first;   // first local pixel-sample of the chunk (index into batch*rows*w)
+  int count;         // valid pixel-samples in the chunk
+  int padded;        // rows allocated (multiple of 128); rows >= count are written as zeros
+};
+
+__device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int& r, int& c) {
+  long long per = (long long)g.rows * g.w;
+  b = (int)(i / per);
+  int rem = (int)(i - (long long)b * per);
+  r = rem / g.w + g.row_offset;
+  c = rem - (rem / g.w) * g.w;
+}
+
 // Programmatic dependent launch: block until every kernel this launch depends on has completed and flushed.
 // A no-op for launches without the programmatic-stream-serialization attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

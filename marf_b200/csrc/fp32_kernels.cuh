@@ -174,20 +174,6 @@ static __global__ void k_warp_corners(Geo g, const float* __restrict__ Hm, int n
 // encoding prologue: grid -> warp -> [u, v, w_k sin(f_k u), w_k cos(f_k u), w_k sin(f_k v), w_k cos(f_k v)]
 // (warp.py:33-81, model/planar.py:451-471,434).  One thread per pixel-sample; X0 is [n_pad, ld].
 // ============================================================================================
-struct PxRange {
-  long long first;   // first local pixel-sample of the chunk (index into batch*rows*w)
-  int count;         // valid pixel-samples in the chunk
-  int padded;        // rows allocated (multiple of 128); rows >= count are written as zeros
-};
-
-__device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int& r, int& c) {
-  long long per = (long long)g.rows * g.w;
-  b = (int)(i / per);
-  int rem = (int)(i - (long long)b * per);
-  r = rem / g.w + g.row_offset;
-  c = rem - (rem / g.w) * g.w;
-}
-
 static __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm /* [batch_global,9] or identity */,
                          int identity, float* __restrict__ X0, int ld) {
   pdl_wait();

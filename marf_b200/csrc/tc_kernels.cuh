@@ -10,6 +10,7 @@
 #pragma once
 #include <cuda_bf16.h>
 
+#include "common.cuh"
 #include "tc_ptx.cuh"
 
 namespace marf {
@@ -22,7 +23,7 @@ constexpr int kStages = 4;
 constexpr int kThreads = 320;         // k_tc_gemm: producer warp, MMA warp, 8 epilogue warps
 constexpr int kDwThreads = 192;       // k_tc_dw: producer warp, MMA warp, 4 epilogue warps
 
-enum { EPI_BIAS_RELU = 0, EPI_RELU_MASK = 1, EPI_PLAIN_F32 = 2 };
+enum { EPI_BIAS_RELU = 0, EPI_RELU_MASK = 1, EPI_PLAIN_F32 = 2, EPI_WARP_GRAD = 3 };
 
 struct GemmParams {
   int n_tiles;          // 128-row tiles
@@ -38,6 +39,13 @@ struct GemmParams {
   unsigned long long load_policy;   // L2 cache hint of the streamed A tiles
   unsigned long long store_policy;  // L2 cache hint of the output tiles
   int prefetch_ahead;   // tiles to prefetch into L2 ahead of the SMEM ring (0 = off)
+  // EPI_WARP_GRAD (N_TILE = 64): the tile is dL/d(encoded input); the epilogue runs the backward of the posenc + homography
+  // prologue per pixel and reduces the per-patch 3x3 Jacobian G (fp64 atomics), nothing is stored per pixel
+  Geo geo;
+  PxRange rg;
+  const float* Hm;      // [batch_global, 9]
+  double* G;            // [batch, 9]
+  int wg_split;         // 1: epilogue group 0 handles the u half of the encoding, group 1 the v half; 0: group 0 does both
   long long* trace;     // diagnostics: per-tile clock64() stamps of CTA 0 ([tile_iter][16]); nullptr in production
 };
 
@@ -86,11 +94,11 @@ __device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int N_TILE, int EPI>
+template <int N_TILE, int EPI, int LT = 0>   // LT: compile-time posenc band count for EPI_WARP_GRAD (0: runtime)
 __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__ GemmJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr bool kStaged = EPI != EPI_PLAIN_F32;
+  constexpr bool kStaged = EPI != EPI_PLAIN_F32 && EPI != EPI_WARP_GRAD;
   constexpr int kSlabs = N_TILE / 64;
   constexpr uint32_t kTmemCols = 2 * N_TILE < 32 ? 32 : 2 * N_TILE;
   int jr = 0;
@@ -231,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       if (tr) p.trace[t_iter * 16 + 3 + grp * 6] = clock64();
 #pragma unroll
       for (int j = 0; j < kSlabs; ++j) {
-        if ((j & 1) != grp) continue;
+        if ((EPI != EPI_WARP_GRAD || !p.wg_split) && (j & 1) != grp) continue;   // (split EPI_WARP_GRAD: both groups share slab 0)
         uint32_t v[64];
         {
           uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -246,7 +254,72 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
         }
         tmem_ld_wait();
         if (tr) p.trace[t_iter * 16 + 4 + grp * 6 + (j >> 1) * 2] = clock64();
-        if (EPI == EPI_PLAIN_F32) {
+        if (EPI == EPI_WARP_GRAD) {
+          const int t = tile * kTileM + r;
+          const bool valid = t < p.rg.count;
+          int b = -1;
+          float acc[9];
+#pragma unroll
+          for (int i = 0; i < 9; ++i) acc[i] = 0.f;
+          if (valid) {
+            int rr, cc;
+            decode_px(p.geo, p.rg.first + t, b, rr, cc);
+            float x, y, u, vv, qz;
+            grid_xy(p.geo, rr, cc, x, y);
+            apply_h(p.Hm + 9 * (b + p.geo.patch_offset), x, y, u, vv, qz);
+            // the two epilogue groups split the work: group 0 differentiates the u half of the encoding, group 1 the v half
+            const bool do_u = !p.wg_split || grp == 0, do_v = !p.wg_split || grp == 1;
+            float gu = do_u ? __uint_as_float(v[0]) : 0.f, gv = do_v ? __uint_as_float(v[1]) : 0.f;
+            const int Lb = LT > 0 ? LT : p.geo.L;
+#pragma unroll
+            for (int k = 0; k < (LT > 0 ? LT : 15); ++k) {
+              if (k < Lb) {
+                float su = 0.f, cu = 0.f, sv = 0.f, cv = 0.f;
+                const float f = p.geo.band_f[k];
+                if (do_u) sincosf(u * f, &su, &cu);
+                if (do_v) sincosf(vv * f, &sv, &cv);
+                const float wf = p.geo.band_w[k] * f;
+                float d_su = 0.f, d_cu = 0.f, d_sv = 0.f, d_cv = 0.f;
+                if (LT > 0) {                          // static register indices
+                  d_su = __uint_as_float(v[(2 + k) & 63]);
+                  d_cu = __uint_as_float(v[(2 + LT + k) & 63]);
+                  d_sv = __uint_as_float(v[(2 + 2 * LT + k) & 63]);
+                  d_cv = __uint_as_float(v[(2 + 3 * LT + k) & 63]);
+                } else {                               // runtime L: select with an unrolled scan
+#pragma unroll
+                  for (int c2 = 2; c2 < 62; ++c2) {
+                    const float val = __uint_as_float(v[c2]);
+                    if (c2 == 2 + k) d_su = val;
+                    if (c2 == 2 + Lb + k) d_cu = val;
+                    if (c2 == 2 + 2 * Lb + k) d_sv = val;
+                    if (c2 == 2 + 3 * Lb + k) d_cv = val;
+                  }
+                }
+                gu += wf * (d_su * cu - d_cu * su);
+                gv += wf * (d_sv * cv - d_cv * sv);
+              }
+            }
+            const float inv = 1.0f / qz;
+            const float dq0 = gu * inv, dq1 = gv * inv, dq2 = -(gu * u + gv * vv) * inv;
+            acc[0] = dq0 * x; acc[1] = dq0 * y; acc[2] = dq0;
+            acc[3] = dq1 * x; acc[4] = dq1 * y; acc[5] = dq1;
+            acc[6] = dq2 * x; acc[7] = dq2 * y; acc[8] = dq2;
+          }
+          const int b0 = __shfl_sync(0xffffffffu, b, 0);
+          const bool uniform = __all_sync(0xffffffffu, b == b0 || b < 0);
+          if (uniform) {
+            if (b0 >= 0) {
+#pragma unroll
+              for (int i = 0; i < 9; ++i) {
+                const float sacc = warp_sum(acc[i]);
+                if (lane == 0) atomicAdd(&p.G[9 * b0 + i], (double)sacc);
+              }
+            }
+          } else if (valid) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) atomicAdd(&p.G[9 * b + i], (double)acc[i]);
+          }
+        } else if (EPI == EPI_PLAIN_F32) {
           float* o = p.out_f32 + (size_t)(tile * kTileM + r) * p.ld_out + n0 + j * 64;
 #pragma unroll
           for (int c4 = 0; c4 < 16; ++c4)
