@@ -614,6 +614,40 @@ bool bf16_supported(const marf_handle* h, const marf_step_io*, std::string* why)
 }
 
 // ------------------------------------------------------------------------------------------------ launches
+// diagnostics (MARF_TC_TRACE=<n>): dump per-tile clock64 stamps of the first CTA of every job of the n-th traced launch
+struct TraceCtx { long long* dev = nullptr; int iters = 0; int njobs = 0; };
+static TraceCtx trace_begin(tc::GemmJobs& jobs) {
+  TraceCtx t;
+  static int calls = 0;
+  const char* e = getenv("MARF_TC_TRACE");
+  if (!e || ++calls != atoi(e)) return t;
+  t.njobs = jobs.n;
+  for (int i = 0; i < jobs.n; ++i) t.iters = std::max(t.iters, (jobs.j[i].p.n_tiles + jobs.j[i].cta_count - 1) / jobs.j[i].cta_count);
+  cudaMalloc(&t.dev, (size_t)jobs.n * t.iters * 16 * sizeof(long long));
+  cudaMemset(t.dev, 0, (size_t)jobs.n * t.iters * 16 * sizeof(long long));
+  for (int i = 0; i < jobs.n; ++i) jobs.j[i].p.trace = t.dev + (size_t)i * t.iters * 16;
+  return t;
+}
+static void trace_end(const TraceCtx& t, cudaStream_t st, const char* what) {
+  if (!t.dev) return;
+  cudaStreamSynchronize(st);
+  std::vector<long long> tr((size_t)t.njobs * t.iters * 16);
+  cudaMemcpy(tr.data(), t.dev, tr.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < t.njobs; ++i) {
+    long long t00 = tr[(size_t)i * t.iters * 16 + 1];
+    fprintf(stderr, "trace %s job %d: iter | prod mma_start mma_commit | g0 acc_full ld0 st0 ld1 st1 | g1 acc_full ld0 st0 ld1 st1\n", what, i);
+    for (int it = 0; it < t.iters; ++it) {
+      fprintf(stderr, "%3d |", it);
+      for (int k = 0; k < 15; ++k) {
+        long long v = tr[((size_t)i * t.iters + it) * 16 + k];
+        fprintf(stderr, " %7lld", v ? v - t00 : -1);
+      }
+      fprintf(stderr, "\n");
+    }
+  }
+  cudaFree(t.dev);
+}
+
 // distribute the launch's CTAs over the jobs in proportion to `weight` (>= 1 CTA each), at most n_tiles per job
 static void assign_ctas(tc::GemmJobs& jobs, const int* weight, int num_sms) {
   int wsum = 0;
@@ -708,8 +742,10 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
     assign_ctas(jobs, w, S->num_sms);
     int smem = tc::gemm_smem(256, max_kc, true).total + 1024;
     int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
+    TraceCtx tr = trace_begin(jobs);
     launch_k(tc::k_tc_gemm<256, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
     BF_LAUNCH(h);
+    trace_end(tr, st, "fwd");
   }
   return MARF_OK;
 }
