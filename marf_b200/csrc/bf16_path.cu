@@ -10,6 +10,7 @@
 #include "engine.cuh"
 #include "fp32_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_chain.cuh"
 
 namespace marf {
 
@@ -384,7 +385,7 @@ static __global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, f
 }
 
 // table-driven (un)packing: one launch for every layer of both networks
-struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode, src_ld, col_off; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed
+struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode, src_ld, col_off; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed, 3: bf16 hi rows [0,8) / lo rows [8,16)
 constexpr int kMaxPack = 48;
 struct PackTable { PackEntry e[kMaxPack]; int n; };
 static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
@@ -394,7 +395,9 @@ static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
     int pr = i / E.pcol, pc = i - pr * E.pcol;
     int r = E.mode == 2 ? pc : pr, c = E.mode == 2 ? pr : pc;
+    if (E.mode == 3) r = pr & 7;
     float v = (r < E.rows && c < E.cols) ? E.src[(size_t)r * E.src_ld + E.col_off + c] : 0.f;
+    if (E.mode == 3 && pr >= 8) v -= __bfloat162float(__float2bfloat16(v));     // the part the hi row misses
     if (E.mode == 0) reinterpret_cast<float*>(E.dst)[i] = v;
     else reinterpret_cast<bf16*>(E.dst)[i] = __float2bfloat16(v);
   }
@@ -423,6 +426,7 @@ struct BfLayer {
   bf16* Wk = nullptr;    // [np, kp]   forward B operand (K-major)
   bf16* Wt = nullptr;    // [kp, np]   dX B operand (K-major over out features)
   CUtensorMap tmWk, tmWt;
+  CUtensorMap tmWk128, tmWt128;   // 128-row boxes: the weight chunks of the fused chain kernel
 };
 
 struct BfChain {
@@ -442,7 +446,10 @@ struct BfChain {
   bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW / dX
   CUtensorMap tmDL64, tmDL128;
   bf16* Wlast_t = nullptr;                // [k_in(last), 64] bf16: W_last^T zero padded (B operand of the output layer's dX GEMM)
-  CUtensorMap tmWlast_t;
+  CUtensorMap tmWlast_t, tmWlast128;
+  bf16* Wout16 = nullptr;                 // [16, k_in(last)] bf16: rows 0..7 hi, 8..15 lo halves of W_last (fused chain output layer)
+  CUtensorMap tmWout16;
+  bool fused = false;                     // shape served by k_tc_chain: 64 -> 256 x4 -> (<=4)
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
   int col_off0 = 0;                       // class-table mode: layer 0 uses columns [col_off0, col_off0 + k_in) of W0
@@ -507,6 +514,10 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
       if (rc) return rc;
       rc = make_tmap(h, S, &L.tmWt, L.Wt, L.kp, L.np, std::min(L.kp, 256));
       if (rc) return rc;
+      rc = make_tmap(h, S, &L.tmWk128, L.Wk, L.np, L.kp, std::min(L.np, 128));
+      if (rc) return rc;
+      rc = make_tmap(h, S, &L.tmWt128, L.Wt, L.kp, L.np, std::min(L.kp, 128));
+      if (rc) return rc;
     } else if (l != F.n - 1) {
       return fail(h, MARF_ERR_UNSUPPORTED, "bf16: thin hidden layers are not supported");
     } else if (L.k_in != 256 && L.k_in != 512) {
@@ -554,6 +565,16 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     B.Wlast_t = (bf16*)ws_alloc(h, (size_t)kl * 64 * 2);
     if (!B.Wlast_t) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (output layer)");
     rc = make_tmap(h, S, &B.tmWlast_t, B.Wlast_t, kl, 64, 256);
+    if (rc) return rc;
+    rc = make_tmap(h, S, &B.tmWlast128, B.Wlast_t, kl, 64, 128);
+    if (rc) return rc;
+    B.Wout16 = (bf16*)ws_alloc(h, (size_t)16 * kl * 2);
+    if (!B.Wout16) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (output layer)");
+    rc = make_tmap(h, S, &B.tmWout16, B.Wout16, 16, kl, 16);
+    if (rc) return rc;
+    bool ok = B.n - 1 == tc::kChUnits && B.L[0].kp == 64 && B.L[B.n - 1].k_out <= 4;
+    for (int l = 0; l < B.n - 1; ++l) ok = ok && B.L[l].np == 256 && (l == 0 || B.L[l].kp == 256);
+    B.fused = ok && getenv("MARF_NO_FUSE") == nullptr;
   }
   return rc;
 }
@@ -571,6 +592,8 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1 * 512 + 1) * 4));
   return MARF_OK;
@@ -750,6 +773,42 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
   return MARF_OK;
 }
 
+// dX0 of the chains that need the gradient w.r.t. their input: the epilogue is the backward of the encoding prologue
+static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, PxRange rg) {
+  Bf16State* S = h->bf16;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    if (!B.need_dx0) continue;
+    BfLayer& L = B.L[0];
+    if (L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX0: encoded input must fit 64 columns");
+    tc::GemmJobs one{};
+    one.n = 1;
+    tc::GemmJob& J = one.j[0];
+    J.tmA = B.tmDY128[0];
+    J.tmW = L.tmWt;
+    J.tmOut = B.tmDY128[0];
+    J.p.n_tiles = rows / 128;
+    J.p.k_chunks = L.np / 64;
+    J.p.load_policy = tc::kEvictNormal;
+    J.p.store_policy = tc::kEvictNormal;
+    J.p.geo = h->geo;
+    J.p.rg = rg;
+    J.p.Hm = h->Hm;
+    J.p.G = h->G;
+    J.p.wg_split = getenv("MARF_WG_SPLIT") ? 1 : 0;       // measured: one group doing both halves is faster
+    J.cta_begin = 0;
+    J.cta_count = std::min(J.p.n_tiles, S->num_sms);
+    int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
+    // the epilogue is the backward of the encoding prologue (SURVEY.md §8 a-4, a-5): per-pixel (g_u, g_v) -> dq -> per-patch G
+    if (h->geo.L == 8) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 8>, J.cta_count, tc::kThreads, smem, st, one);
+    else if (h->geo.L == 10) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 10>, J.cta_count, tc::kThreads, smem, st, one);
+    else if (h->geo.L == 4) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, J.cta_count, tc::kThreads, smem, st, one);
+    else launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, J.cta_count, tc::kThreads, smem, st, one);
+    BF_LAUNCH(h);
+  }
+  return MARF_OK;
+}
+
 // dX of every tensor-core layer l >= 1 of the given chains in ONE launch (dY[l-1] = (dY[l] W_l) * relu_mask(act[l])),
 // chained through per-tile flags; then dX0 of the chains that need the gradient w.r.t. their input.
 static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, PxRange rg) {
@@ -797,37 +856,7 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, grid, tc::kThreads, smem, st, jobs);
     BF_LAUNCH(h);
   }
-  for (int ci = 0; ci < n_chains; ++ci) {
-    BfChain& B = *chains[ci];
-    if (!B.need_dx0) continue;
-    BfLayer& L = B.L[0];
-    if (L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX0: encoded input must fit 64 columns");
-    tc::GemmJobs one{};
-    one.n = 1;
-    tc::GemmJob& J = one.j[0];
-    J.tmA = B.tmDY128[0];
-    J.tmW = L.tmWt;
-    J.tmOut = B.tmDY128[0];
-    J.p.n_tiles = rows / 128;
-    J.p.k_chunks = L.np / 64;
-    J.p.load_policy = tc::kEvictNormal;
-    J.p.store_policy = tc::kEvictNormal;
-    J.p.geo = h->geo;
-    J.p.rg = rg;
-    J.p.Hm = h->Hm;
-    J.p.G = h->G;
-    J.p.wg_split = getenv("MARF_WG_SPLIT") ? 1 : 0;       // measured: one group doing both halves is faster
-    J.cta_begin = 0;
-    J.cta_count = std::min(J.p.n_tiles, S->num_sms);
-    int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
-    // the epilogue is the backward of the encoding prologue (SURVEY.md §8 a-4, a-5): per-pixel (g_u, g_v) -> dq -> per-patch G
-    if (h->geo.L == 8) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 8>, J.cta_count, tc::kThreads, smem, st, one);
-    else if (h->geo.L == 10) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 10>, J.cta_count, tc::kThreads, smem, st, one);
-    else if (h->geo.L == 4) launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, J.cta_count, tc::kThreads, smem, st, one);
-    else launch_k(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, J.cta_count, tc::kThreads, smem, st, one);
-    BF_LAUNCH(h);
-  }
-  return MARF_OK;
+  return launch_dx0(h, st, chains, n_chains, rows, rg);
 }
 
 // all dW / db of the tensor-core layers of the given chains: one launch per N-tile width
@@ -900,6 +929,52 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
     BF_LAUNCH(h);
   }
+  return MARF_OK;
+}
+
+
+// ---- fused chains (tc_chain.cuh): all hidden layers (+ output layer) of up to two MLPs in ONE launch
+static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, bool forward) {
+  Bf16State* S = h->bf16;
+  tc::ChainJobs jobs{};
+  jobs.n = n_chains;
+  jobs.n_tiles = rows / 128;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    tc::ChainJob& J = jobs.c[ci];
+    const int n = B.n;                       // n - 1 hidden layers + the thin output layer
+    J.bits_ld = 256 / 32;
+    if (forward) {
+      J.tmIn = B.tmAct128[0];
+      J.tmWout = B.tmWout16;
+      for (int u = 0; u < tc::kChUnits; ++u) {
+        J.u[u].tmW = B.L[u].tmWk128;
+        J.u[u].tmOut = B.tmAct128[u + 1];
+        J.u[u].bias = (u == 0 && B.col_off0 > 0) ? B.zero_bias : B.f32->bp[u];   // (class-table mode: b0 lives in Wk)
+        J.u[u].bits = B.bits[u + 1];
+      }
+      J.bias_out = B.f32->bp[n - 1];
+      J.logits = B.logits;
+      J.k_out = B.L[n - 1].k_out;
+    } else {
+      // unit 0: dY[n-2] = (dlogits W_last) * mask(act[n-1]); unit u >= 1: layer l = n-1-u, dY[l-1] = (dY[l] W_l) * mask(act[l])
+      J.tmIn = B.tmDL128;
+      J.tmWout = B.tmWout16;                 // unused
+      for (int u = 0; u < tc::kChUnits; ++u) {
+        const int l = n - 1 - u;
+        J.u[u].tmW = u == 0 ? B.tmWlast128 : B.L[l].tmWt128;
+        J.u[u].tmOut = B.tmDY128[l - 1];
+        J.u[u].bias = nullptr;
+        J.u[u].bits = B.bits[l];
+      }
+    }
+  }
+  const int n_items = (jobs.n_tiles + 1) / 2 * n_chains;
+  const int grid = std::min(n_items, S->num_sms);
+  const int smem = tc::kChSmem + 1024;
+  if (forward) launch_k(tc::k_tc_chain<tc::CH_FWD>, grid, tc::kChThreads, smem, st, jobs);
+  else launch_k(tc::k_tc_chain<tc::CH_DX>, grid, tc::kChThreads, smem, st, jobs);
+  BF_LAUNCH(h);
   return MARF_OK;
 }
 
@@ -990,9 +1065,10 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
     Chain& F = *B.f32;
     for (int l = 0; l < B.n; ++l) {
       if (!Ws[ci][l] || !bs[ci][l]) return fail(h, MARF_ERR_INVALID, "null layer parameter");
-      if (t.n + 3 > kMaxPack) return fail(h, MARF_ERR_UNSUPPORTED, "too many layers");
+      if (t.n + 4 > kMaxPack) return fail(h, MARF_ERR_UNSUPPORTED, "too many layers");
       add(bs[ci][l], F.bp[l], 1, F.k_out[l], 1, F.ld_out[l], 0);
       if (B.L[l].thin && B.Wlast_t) add(Ws[ci][l], B.Wlast_t, B.L[l].k_out, B.L[l].k_in, B.L[l].k_in, 64, 2);
+      if (B.L[l].thin && B.Wout16) add(Ws[ci][l], B.Wout16, B.L[l].k_out, B.L[l].k_in, 16, B.L[l].k_in, 3);
       if (B.L[l].thin) continue;
       // (layer 0 of the mask head only multiplies the uv columns: a window of the caller's [k_out, k_in] matrix)
       const int off = l == 0 ? B.col_off0 : 0;
@@ -1074,15 +1150,23 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
   // chain after chain, each followed at once by its output layer: the last hidden activation is still in L2
   BfChain* c_img[1] = {&S->img};
   BfChain* c_msk[1] = {&S->msk};
-  int rc = launch_forward_all(h, st, c_img, 1, rg.padded);
-  if (rc) return rc;
-  rc = thin_fwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1], io->mlp_b[c.n_layers - 1]);
-  if (rc) return rc;
-  if (implicit) {
-    rc = launch_forward_all(h, st, c_msk, 1, rg.padded);
+  int rc = MARF_OK;
+  if (S->img.fused && (!implicit || S->msk.fused)) {
+    // layer-fused: every hidden layer and the output layer of both networks in one launch, activations resident in SMEM
+    BfChain* both[2] = {&S->img, &S->msk};
+    rc = launch_chain(h, st, both, implicit ? 2 : 1, rg.padded, true);
     if (rc) return rc;
-    rc = thin_fwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1], io->mask_b[c.mask_n_layers - 1]);
+  } else {
+    rc = launch_forward_all(h, st, c_img, 1, rg.padded);
     if (rc) return rc;
+    rc = thin_fwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1], io->mlp_b[c.n_layers - 1]);
+    if (rc) return rc;
+    if (implicit) {
+      rc = launch_forward_all(h, st, c_msk, 1, rg.padded);
+      if (rc) return rc;
+      rc = thin_fwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1], io->mask_b[c.mask_n_layers - 1]);
+      if (rc) return rc;
+    }
   }
   if (stats) {
     LossArgs a;
@@ -1119,15 +1203,24 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   BF_LAUNCH(h);
   BfChain* c_img[1] = {&S->img};
   BfChain* c_msk[1] = {&S->msk};
-  int rc = thin_bwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
-  if (rc) return rc;
-  rc = launch_dx_all(h, st, c_img, 1, rg.padded, rg);       // ends with dX0 + encoding backward -> per-patch G
-  if (rc) return rc;
-  if (implicit) {
-    rc = thin_bwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
+  int rc = MARF_OK;
+  if (S->img.fused && (!implicit || S->msk.fused)) {
+    BfChain* both[2] = {&S->img, &S->msk};
+    rc = launch_chain(h, st, both, implicit ? 2 : 1, rg.padded, false);   // dlogits -> dY[n-2] -> ... -> dY[0], one launch
     if (rc) return rc;
-    rc = launch_dx_all(h, st, c_msk, 1, rg.padded, rg);
+    rc = launch_dx0(h, st, c_img, 1, rg.padded, rg);                      // dX0 + encoding backward -> per-patch G
     if (rc) return rc;
+  } else {
+    rc = thin_bwd(h, st, S->img, rg.padded, io->mlp_w[c.n_layers - 1]);
+    if (rc) return rc;
+    rc = launch_dx_all(h, st, c_img, 1, rg.padded, rg);       // ends with dX0 + encoding backward -> per-patch G
+    if (rc) return rc;
+    if (implicit) {
+      rc = thin_bwd(h, st, S->msk, rg.padded, io->mask_w[c.mask_n_layers - 1]);
+      if (rc) return rc;
+      rc = launch_dx_all(h, st, c_msk, 1, rg.padded, rg);
+      if (rc) return rc;
+    }
   }
   BfChain* chains[2] = {&S->img, &S->msk};
   return launch_dw_all(h, st, chains, implicit ? 2 : 1, rg.padded, rg.first);

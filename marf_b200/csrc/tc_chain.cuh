@@ -1,0 +1,355 @@
+// Layer-fused tcgen05 chain kernel of the bf16 path (sm_100a).
+//
+//   k_tc_chain<CH_FWD> : X_{l+1} = relu(X_l W_l^T + b_l) for the four 256-wide hidden layers of an MLP, then the
+//                        3-/1-wide output layer, for a PAIR of 128-row tiles per pass.  The activations of the pair stay
+//                        in SMEM between the layers (written in place by the epilogue, in the SWIZZLE_128B K-major
+//                        layout the next layer's MMA reads); every layer's output is still TMA-stored to HBM once
+//                        because the dW pass needs it, but nothing is read back: HBM traffic per pixel-sample is
+//                        128 B in + 4 x 512 B out instead of 4 x (512 B in + 512 B out).
+//   k_tc_chain<CH_DX>  : dY_{l-1} = (dY_l W_l) * relu_mask(X_l) from the output-layer gradient down to dY_0, same scheme.
+//
+// The weights do not fit in SMEM next to the activations, so they stream from L2 through a 4-stage TMA ring as
+// [128 output features x 64 K] chunks; one chunk feeds the MMAs of both tiles (so 64 KB of weights per tile-layer).
+// A layer is issued as two output halves h (128 columns each, accumulators acc[tile][h] = the 512 TMEM columns):
+// while the epilogue drains half h, the MMAs of the other half / of the next layer run.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// (group g = (warp-2)/4 owns tile g of the pair, warp%4 = TMEM lane quarter, thread = tile row).
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace marf {
+namespace tc {
+
+enum { CH_FWD = 0, CH_DX = 1 };
+
+constexpr int kChThreads = 320;
+constexpr int kChUnits = 4;                   // hidden units of a chain: 64 -> 256 -> 256 -> 256 -> 256
+constexpr int kChWStages = 4;
+constexpr int kChWStage = 128 * 128;          // [128 features x 64 K] bf16
+constexpr int kChSlab = kChunkBytes;          // [128 rows x 64 cols] bf16 = 16 KB
+constexpr int kChActOff = 0;                  // act[2 tiles][4 slabs]
+constexpr int kChWOff = 2 * 4 * kChSlab;      // W ring
+constexpr int kChInOff = kChWOff + kChWStages * kChWStage;   // in[2 tiles]: the 64-wide input of unit 0
+constexpr int kChBarOff = kChInOff + 2 * kChSlab;
+constexpr int kChSmem = kChBarOff + 256;
+
+struct alignas(64) ChainUnit {
+  CUtensorMap tmW;        // box {64, 128} over the unit's weights [256 features, K]
+  CUtensorMap tmOut;      // box {64, 128} over the unit's output [rows, 256]
+  const float* bias;      // CH_FWD: [256]
+  uint32_t* bits;         // CH_FWD: ReLU mask of the output (written); CH_DX: ReLU mask applied to the output (read)
+};
+struct alignas(64) ChainJob {
+  CUtensorMap tmIn;       // box {64, 128} over the 64-wide input of unit 0 [rows, 64]
+  CUtensorMap tmWout;     // CH_FWD: box {64, 16} over the output layer's [16, 256] hi/lo weight rows
+  ChainUnit u[kChUnits];
+  const float* bias_out;  // CH_FWD: [k_out]
+  float* logits;          // CH_FWD: [rows, 4] fp32
+  int k_out;              // CH_FWD: 3 or 1
+  int bits_ld;            // words per row of the mask arrays (= 8)
+};
+struct ChainJobs {
+  ChainJob c[2];
+  int n;                  // chains in this launch
+  int n_tiles;            // 128-row tiles per chain
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constant__ ChainJobs jobs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool kOut = MODE == CH_FWD;          // the forward chain ends with the thin output layer
+  const uint32_t s_act = smem_u32(smem + kChActOff);
+  const uint32_t s_w = smem_u32(smem + kChWOff);
+  const uint32_t s_in = smem_u32(smem + kChInOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChBarOff);
+  uint64_t* w_full = bars;                       // [4]
+  uint64_t* w_empty = bars + 4;                  // [4]
+  uint64_t* in_full = bars + 8;
+  uint64_t* in_empty = bars + 9;
+  uint64_t* acc_full = bars + 10;                // [2]  (per output half)
+  uint64_t* epi_done = bars + 12;                // [2]  (per output half): accumulators drained, output slabs written
+  uint64_t* slab01_free = bars + 14;             // the MMAs that read slabs 0,1 of the current layer input are complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = (jobs.n_tiles + 1) >> 1;
+  const int n_items = n_pairs * jobs.n;
+
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < jobs.n; ++c) {
+      prefetch_tmap(&jobs.c[c].tmIn);
+      for (int u = 0; u < kChUnits; ++u) { prefetch_tmap(&jobs.c[c].u[u].tmW); prefetch_tmap(&jobs.c[c].u[u].tmOut); }
+      if (kOut) prefetch_tmap(&jobs.c[c].tmWout);
+    }
+    for (int s = 0; s < kChWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, 1);
+    for (int h = 0; h < 2; ++h) { mbar_init(&acc_full[h], 1); mbar_init(&epi_done[h], 8); }
+    mbar_init(slab01_free, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernels' output
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t wit = 0, n_in = 0;
+      auto load_w = [&](const CUtensorMap* tm, int k, int h) {
+        const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+        mbar_wait(&w_empty[s], ph ^ 1);
+        mbar_expect_tx(&w_full[s], kChWStage);
+        tma_load_2d_hint(smem + kChWOff + s * kChWStage, tm, k * kChunkK, h * 128, &w_full[s], kEvictLast);
+        ++wit;
+      };
+      auto load_in = [&](int item) {
+        const ChainJob& J = jobs.c[item / n_pairs];
+        const int tile0 = 2 * (item % n_pairs);
+        const bool two = tile0 + 1 < jobs.n_tiles;
+        mbar_wait(in_empty, (n_in & 1) ^ 1);
+        mbar_expect_tx(in_full, two ? 2 * kChSlab : kChSlab);
+        tma_load_2d_hint(smem + kChInOff, &J.tmIn, 0, tile0 * kTileM, in_full, kEvictFirst);
+        if (two) tma_load_2d_hint(smem + kChInOff + kChSlab, &J.tmIn, 0, (tile0 + 1) * kTileM, in_full, kEvictFirst);
+        ++n_in;
+      };
+      if ((int)blockIdx.x < n_items) load_in(blockIdx.x);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const ChainJob& J = jobs.c[item / n_pairs];
+        load_w(&J.u[0].tmW, 0, 0);
+        load_w(&J.u[0].tmW, 0, 1);
+        for (int u = 1; u < kChUnits; ++u) {
+          for (int h = 0; h < 2; ++h)
+            for (int k = 0; k < 4; ++k) load_w(&J.u[u].tmW, k, h);
+          // the next pair's input as soon as unit 0 of this pair has consumed the buffer (in_empty): long before it is needed
+          if (u == 1 && item + (int)gridDim.x < n_items) load_in(item + gridDim.x);
+        }
+        if (kOut) {
+          const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_expect_tx(&w_full[s], 4 * 2048);
+          for (int k = 0; k < 4; ++k)
+            tma_load_2d_hint(smem + kChWOff + s * kChWStage + k * 2048, &J.tmWout, k * kChunkK, 0, &w_full[s], kEvictLast);
+          ++wit;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = idesc_bf16(kTileM, 128, 0, 0);
+      constexpr uint32_t idesc_out = idesc_bf16(kTileM, 16, 0, 0);
+      uint32_t wit = 0, n_in = 0, c_epi0 = 0, c_epi1 = 0;
+      auto wait_epi = [&](int h) {
+        mbar_wait(&epi_done[h], (h ? c_epi1 : c_epi0) & 1);
+        if (h) ++c_epi1; else ++c_epi0;
+        tc_fence_after();
+      };
+      // one weight chunk against the same K slab of both tiles
+      auto mma_chunk = [&](uint32_t a0, uint32_t a1, bool two, int h, bool first) {
+        const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+        mbar_wait(&w_full[s], ph);
+        tc_fence_after();
+        const uint64_t db = smem_desc_sw128(s_w + s * kChWStage, 16, 1024);
+        const uint64_t d0 = smem_desc_sw128(a0, 16, 1024);
+        const uint64_t d1 = smem_desc_sw128(a1, 16, 1024);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + h * 128, d0 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + 256 + h * 128, d1 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
+        }
+        umma_commit(&w_empty[s]);
+        ++wit;
+      };
+      bool first_item = true;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, first_item = false) {
+        const int tile0 = 2 * (item % n_pairs);
+        const bool two = tile0 + 1 < jobs.n_tiles;
+        // ---- unit 0: K = 64 from the input buffer
+        mbar_wait(in_full, n_in & 1);
+        ++n_in;
+        tc_fence_after();
+        if (!first_item && !kOut) wait_epi(0);          // acc[.][0] drained (last unit of the previous pair)
+        mma_chunk(s_in, s_in + kChSlab, two, 0, true);
+        umma_commit(&acc_full[0]);
+        if (!first_item) wait_epi(1);                   // acc[.][1] drained (output unit / last unit of the previous pair)
+        mma_chunk(s_in, s_in + kChSlab, two, 1, true);
+        umma_commit(&acc_full[1]);
+        umma_commit(in_empty);
+        // ---- units 1..3: K = 256 from the activation slabs the previous unit's epilogue wrote in place
+        for (int u = 1; u < kChUnits; ++u) {
+          wait_epi(0);                                  // slabs 0,1 written, acc[.][0] drained
+          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, two, 0, true);
+          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, two, 0, false);
+          wait_epi(1);                                  // slabs 2,3 written, acc[.][1] drained
+          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, two, 0, false);
+          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, two, 0, false);
+          umma_commit(&acc_full[0]);
+          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, two, 1, true);
+          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, two, 1, false);
+          umma_commit(slab01_free);                     // the half-0 epilogue may now overwrite slabs 0,1
+          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, two, 1, false);
+          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, two, 1, false);
+          umma_commit(&acc_full[1]);
+        }
+        if (kOut) {
+          // ---- output layer: N = 16 (rows 0..7 hi, 8..15 lo halves of the <= 4 real output rows), accumulators in acc[.][1]
+          wait_epi(0);
+          wait_epi(1);
+          const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          for (int t = 0; t < (two ? 2 : 1); ++t)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = smem_desc_sw128(s_act + (t * 4 + k) * kChSlab, 16, 1024);
+              const uint64_t db = smem_desc_sw128(s_w + s * kChWStage + k * 2048, 16, 1024);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + t * 256 + 128, da + 2 * j, db + 2 * j, idesc_out, (k | j) != 0);
+            }
+          umma_commit(&w_empty[s]);
+          ++wit;
+          umma_commit(&acc_full[1]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: group = tile of the pair, thread = row
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const bool gleader = threadIdx.x == 64 + 128 * grp;
+    const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
+    uint32_t c_acc0 = 0, c_acc1 = 0, c_free = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const ChainJob& J = jobs.c[item / n_pairs];
+      const int tile = 2 * (item % n_pairs) + grp;
+      const bool valid = tile < jobs.n_tiles;
+      const size_t grow = (size_t)tile * kTileM + r;
+      for (int u = 0; u < kChUnits; ++u) {
+        const ChainUnit& U = J.u[u];
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint4 mb = make_uint4(0u, 0u, 0u, 0u);
+          if (MODE == CH_DX && valid) mb = *reinterpret_cast<const uint4*>(U.bits + grow * J.bits_ld + h * 4);
+          mbar_wait(&acc_full[h], (h ? c_acc1 : c_acc0) & 1);
+          if (h) ++c_acc1; else ++c_acc0;
+          tc_fence_after();
+          if (valid) {
+            // the TMA stores that read slabs 2h, 2h+1 (this group's second-newest commit group) must have finished reading
+            if (gleader) bulk_wait_read<1>();
+            named_bar_sync(1 + grp, 128);
+          }
+          if (u >= 1 && h == 0) {
+            mbar_wait(slab01_free, c_free & 1);
+            ++c_free;
+          }
+          if (valid) {
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * h + jj;
+              uint32_t v[64];
+              {
+                uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                tmem_ld32(t_lane + h * 128 + jj * 64, v0);
+                tmem_ld32(t_lane + h * 128 + jj * 64 + 32, v1);
+              }
+              const uint32_t ob = s_act + (uint32_t)(grp * 4 + j) * kChSlab + sw_row;
+              uint32_t obits[2] = {0u, 0u};
+              const uint32_t mw[2] = {jj == 0 ? mb.x : mb.z, jj == 0 ? mb.y : mb.w};
+              const float4* bp = reinterpret_cast<const float4*>(U.bias + j * 64);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint32_t w[4];
+                float bv[8];
+                if (MODE == CH_FWD) {
+                  const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+                  bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+                }
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                  const int c = i * 8 + pr * 2;             // column inside the slab
+                  const int t = (c & 31) >> 1;              // pair index inside the 32-column group
+                  float lo = __uint_as_float(v[c]), hi = __uint_as_float(v[c + 1]);
+                  if (MODE == CH_FWD) {
+                    lo += bv[pr * 2];
+                    hi += bv[pr * 2 + 1];
+                    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                    uint32_t gt;
+                    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(w[pr]), "r"(0u));
+                    obits[c >> 5] |= gt & (0x00010001u << t);
+                  } else {
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                    const uint32_t sel = (mw[c >> 5] >> t) & 0x00010001u;
+                    w[pr] &= sel * 0xFFFFu;
+                  }
+                }
+                sts128(ob + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4), w[0], w[1], w[2], w[3]);
+              }
+              if (MODE == CH_FWD)
+                *reinterpret_cast<uint2*>(U.bits + grow * J.bits_ld + j * 2) = make_uint2(obits[0], obits[1]);
+            }
+            fence_proxy_async_smem();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&epi_done[h]);        // the MMA warp may read the slabs / overwrite the accumulators
+          if (valid) {
+            named_bar_sync(3 + grp, 128);                  // all 128 rows of both slabs are in SMEM
+            if (gleader) {
+              tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, kEvictFirst);
+              tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, kEvictFirst);
+              bulk_commit();
+            }
+          }
+        }
+      }
+      if (kOut) {
+        mbar_wait(&acc_full[1], c_acc1 & 1);
+        ++c_acc1;
+        tc_fence_after();
+        if (valid) {
+          uint32_t v[16];
+          tmem_ld16(t_lane + 128, v);
+          tmem_ld_wait();
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = e < J.k_out ? __uint_as_float(v[e]) + __uint_as_float(v[8 + e]) + __ldg(J.bias_out + e) : 0.f;
+          *reinterpret_cast<float4*>(J.logits + grow * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&epi_done[1]);
+      }
+    }
+    if (gleader) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+}  // namespace tc
+}  // namespace marf

@@ -73,6 +73,31 @@ def test_step_bf16_chunked(name):
     eng.close()
 
 
+@pytest.mark.parametrize("name", ["mid_mask_c2f", "implicit_edges"])
+def test_fused_chain_matches_per_layer_kernels(name, monkeypatch):
+    """The layer-fused chain kernel (k_tc_chain: activations resident in SMEM) against the per-layer GEMM launches
+    (MARF_NO_FUSE=1): the hidden layers run the same bf16 MMAs in the same K order, only the 3-/1-wide output layer
+    differs (hi/lo bf16 weight rows on the tensor core instead of fp32 FMAs), so the results agree far below the
+    bf16-vs-oracle tolerance."""
+    import gpu_util
+    cfg, params, images, it, progress, g = cases.build_case(name)
+    eng = gpu_util.make_engine(cfg, "bf16")
+    fused = gpu_util.run_step(eng, cfg, params, images, it, progress)
+    eng.close()
+    monkeypatch.setenv("MARF_NO_FUSE", "1")
+    eng = gpu_util.make_engine(cfg, "bf16")
+    plain = gpu_util.run_step(eng, cfg, params, images, it, progress)
+    eng.close()
+    assert (fused["rgb_pred"] - plain["rgb_pred"]).abs().max().item() <= 2e-4
+    if cfg.use_implicit_mask:
+        assert (fused["mask_pred"] - plain["mask_pred"]).abs().max().item() <= 2e-4
+    for k in ("rgb", "mask", "edge", "all"):
+        assert abs(fused["losses"][k] - plain["losses"][k]) <= 1e-4 * (abs(plain["losses"][k]) + 1e-9), k
+    for k, v in plain["grads"].items():
+        rel = ((fused["grads"][k].double() - v.double()).norm() / (v.double().norm() + 1e-30)).item()
+        assert rel <= 5e-3, (k, rel)
+
+
 def test_bf16_refuses_unsupported_widths_loudly():
     import gpu_util
     from marf_b200 import _lib as L
