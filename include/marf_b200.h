@@ -196,6 +196,10 @@ int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream);
 int marf_tc_selftest(int device, int mode, int rows, int K, int N, const float* A, const float* W, const float* aux,
                      float* out, void* stream);
 
+/* diagnostic: fp32 copy of a resident bf16 buffer of the bf16 path's last chunk (which 0: input of `layer`, [rows, ld];
+ * 1: gradient w.r.t. the output of `layer`, [rows, 256]).  Synchronises `stream`.  Used by tests/ and profiles/tools only. */
+int marf_debug_read_bf16(marf_handle* h, int chain, int which, int layer, float* out, long long rows, void* stream);
+
 /* bookkeeping for bench.py / tests: kernels launched by this handle since creation, bytes of workspace. */
 int64_t marf_launch_count(const marf_handle* h);
 int64_t marf_workspace_bytes(const marf_handle* h);

@@ -972,9 +972,30 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
   const int n_items = (jobs.n_tiles + 1) / 2 * n_chains;
   const int grid = std::min(n_items, S->num_sms);
   const int smem = tc::kChSmem + 1024;
+  // diagnostics (MARF_CHAIN_TRACE=<n>): clock64 stamps of CTA 0 during the n-th chain launch
+  static int calls = 0;
+  const char* te = getenv("MARF_CHAIN_TRACE");
+  const bool tracing = te && ++calls == atoi(te);
+  if (tracing) {
+    cudaMalloc(&jobs.trace, 2 * 4 * 2 * 16 * sizeof(long long));
+    cudaMemset(jobs.trace, 0, 2 * 4 * 2 * 16 * sizeof(long long));
+  }
   if (forward) launch_k(tc::k_tc_chain<tc::CH_FWD>, grid, tc::kChThreads, smem, st, jobs);
   else launch_k(tc::k_tc_chain<tc::CH_DX>, grid, tc::kChThreads, smem, st, jobs);
   BF_LAUNCH(h);
+  if (tracing) {
+    cudaStreamSynchronize(st);
+    long long tr[2 * 4 * 2 * 16];
+    cudaMemcpy(tr, jobs.trace, sizeof(tr), cudaMemcpyDeviceToHost);
+    cudaFree(jobs.trace);
+    const long long t0 = tr[0];
+    fprintf(stderr, "chain trace (%s): item unit half | mma: begin commit mid | g0: acc_full free ld0 ld1 sts arrive+store | g1: ...\n", forward ? "fwd" : "dx");
+    for (int i = 0; i < 2 * 4 * 2; ++i) {
+      fprintf(stderr, "%d %d %d |", i / 8, (i / 2) % 4, i % 2);
+      for (int e = 0; e < 16; ++e) fprintf(stderr, " %6lld", tr[i * 16 + e] ? tr[i * 16 + e] - t0 : -1);
+      fprintf(stderr, "\n");
+    }
+  }
   return MARF_OK;
 }
 
@@ -1289,6 +1310,20 @@ int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
 }  // namespace marf
 
 // ------------------------------------------------------------------------------------------------ diagnostics
+// Copy a resident bf16 buffer of the last chunk to fp32: which 0 = act[layer] (layer input), 1 = dY[layer].  tests/ only.
+extern "C" int marf_debug_read_bf16(marf_handle* h, int chain, int which, int layer, float* out, long long rows, void* stream) {
+  using namespace marf;
+  if (!h || !h->bf16) return MARF_ERR_INVALID;
+  BfChain& B = chain == 0 ? h->bf16->img : h->bf16->msk;
+  if (layer < 0 || layer >= B.n) return MARF_ERR_INVALID;
+  const bf16* src = which == 0 ? B.act[layer] : B.dY[layer];
+  const int ld = which == 0 ? B.ld[layer] : B.L[layer].np;
+  if (!src || rows > h->chunk) return MARF_ERR_INVALID;
+  const long long tot = rows * ld;
+  launch_k(k_bf16_to_f32, (unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream, tot, src, out);
+  return cudaStreamSynchronize((cudaStream_t)stream) == cudaSuccess ? MARF_OK : MARF_ERR_CUDA;
+}
+
 // One tensor-core kernel on caller-provided fp32 device arrays (rounded to bf16 inside), fp32 result.
 //   mode 0: out[rows,N] = relu(A[rows,K] W[N,K]^T + aux[N])          (k_tc_gemm, EPI_BIAS_RELU; bf16-rounded output)
 //   mode 1: out[rows,N] = (A W^T) * (aux[rows,N] > 0)                 (k_tc_gemm, EPI_RELU_MASK; bf16-rounded output)

@@ -25,13 +25,14 @@ enum { CH_FWD = 0, CH_DX = 1 };
 
 constexpr int kChThreads = 320;
 constexpr int kChUnits = 4;                   // hidden units of a chain: 64 -> 256 -> 256 -> 256 -> 256
-constexpr int kChWStages = 4;
+constexpr int kChWStages = 3;
 constexpr int kChWStage = 128 * 128;          // [128 features x 64 K] bf16
 constexpr int kChSlab = kChunkBytes;          // [128 rows x 64 cols] bf16 = 16 KB
 constexpr int kChActOff = 0;                  // act[2 tiles][4 slabs]
 constexpr int kChWOff = 2 * 4 * kChSlab;      // W ring
 constexpr int kChInOff = kChWOff + kChWStages * kChWStage;   // in[2 tiles]: the 64-wide input of unit 0
-constexpr int kChBarOff = kChInOff + 2 * kChSlab;
+constexpr int kChBiasOff = kChInOff + 2 * kChSlab;           // CH_FWD: bias[2 chains][4 units][256] fp32, resident
+constexpr int kChBarOff = kChBiasOff + 2 * kChUnits * 256 * 4;
 constexpr int kChSmem = kChBarOff + 256;
 
 struct alignas(64) ChainUnit {
@@ -53,10 +54,17 @@ struct ChainJobs {
   ChainJob c[2];
   int n;                  // chains in this launch
   int n_tiles;            // 128-row tiles per chain
+  long long* trace;       // diagnostics: clock64() stamps of CTA 0, [item < 2][unit][half][16]; nullptr in production
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
+}
+// (no memory clobber, not volatile: the bias table is written once before the role split, the compiler may hoist these)
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -103,11 +111,16 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernels' output
+  if (MODE == CH_FWD) {
+    float* sb = reinterpret_cast<float*>(smem + kChBiasOff);
+    for (int i = threadIdx.x; i < jobs.n * kChUnits * 256; i += kChThreads)
+      sb[i] = jobs.c[i >> 10].u[(i >> 8) & 3].bias[i & 255];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernels' output
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -157,58 +170,76 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       constexpr uint32_t idesc = idesc_bf16(kTileM, 128, 0, 0);
       constexpr uint32_t idesc_out = idesc_bf16(kTileM, 16, 0, 0);
       uint32_t wit = 0, n_in = 0, c_epi0 = 0, c_epi1 = 0;
+      long long w_wait = 0;
       auto wait_epi = [&](int h) {
         mbar_wait(&epi_done[h], (h ? c_epi1 : c_epi0) & 1);
         if (h) ++c_epi1; else ++c_epi0;
         tc_fence_after();
       };
       // one weight chunk against the same K slab of both tiles
-      auto mma_chunk = [&](uint32_t a0, uint32_t a1, bool two, int h, bool first) {
+      auto mma_chunk = [&](uint32_t a0, uint32_t a1, int h, bool first) {
         const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+        const long long tw0 = jobs.trace ? clock64() : 0;
         mbar_wait(&w_full[s], ph);
+        if (jobs.trace) w_wait += clock64() - tw0;
         tc_fence_after();
         const uint64_t db = smem_desc_sw128(s_w + s * kChWStage, 16, 1024);
         const uint64_t d0 = smem_desc_sw128(a0, 16, 1024);
         const uint64_t d1 = smem_desc_sw128(a1, 16, 1024);
 #pragma unroll
         for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + h * 128, d0 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
-        if (two) {
+        // Tile 1 unconditionally, also when the pair has only one tile (its accumulators are then never read): a branch
+        // here is if-converted by ptxas 12.9 into predicated UTCHMMAs whose descriptor R2URs hang on an unrelated predicate
+        // (observed: stale A/B descriptors, wrong results) — keep every tcgen05.mma of this kernel unconditional.
 #pragma unroll
-          for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + 256 + h * 128, d1 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
-        }
+        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + 256 + h * 128, d1 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
         umma_commit(&w_empty[s]);
         ++wit;
       };
       bool first_item = true;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, first_item = false) {
-        const int tile0 = 2 * (item % n_pairs);
-        const bool two = tile0 + 1 < jobs.n_tiles;
+      int it_no = 0;
+      auto stamp = [&](int u, int h, int e) {
+        if (jobs.trace && blockIdx.x == 0 && it_no < 2) {
+          jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + e] = clock64();
+          if (e == 1) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 3] = jobs.trace[0] + w_wait;   // cumulative wait on weight chunks
+        }
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, first_item = false, ++it_no) {
         // ---- unit 0: K = 64 from the input buffer
         mbar_wait(in_full, n_in & 1);
         ++n_in;
         tc_fence_after();
         if (!first_item && !kOut) wait_epi(0);          // acc[.][0] drained (last unit of the previous pair)
-        mma_chunk(s_in, s_in + kChSlab, two, 0, true);
+        stamp(0, 0, 0);
+        mma_chunk(s_in, s_in + kChSlab, 0, true);
         umma_commit(&acc_full[0]);
+        stamp(0, 0, 1);
         if (!first_item) wait_epi(1);                   // acc[.][1] drained (output unit / last unit of the previous pair)
-        mma_chunk(s_in, s_in + kChSlab, two, 1, true);
+        stamp(0, 1, 0);
+        mma_chunk(s_in, s_in + kChSlab, 1, true);
         umma_commit(&acc_full[1]);
+        stamp(0, 1, 1);
         umma_commit(in_empty);
         // ---- units 1..3: K = 256 from the activation slabs the previous unit's epilogue wrote in place
         for (int u = 1; u < kChUnits; ++u) {
           wait_epi(0);                                  // slabs 0,1 written, acc[.][0] drained
-          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, two, 0, true);
-          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, two, 0, false);
+          stamp(u, 0, 0);
+          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, 0, true);
+          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, 0, false);
           wait_epi(1);                                  // slabs 2,3 written, acc[.][1] drained
-          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, two, 0, false);
-          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, two, 0, false);
+          stamp(u, 0, 2);
+          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, 0, false);
+          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, 0, false);
           umma_commit(&acc_full[0]);
-          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, two, 1, true);
-          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, two, 1, false);
+          stamp(u, 0, 1);
+          stamp(u, 1, 0);
+          mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, 1, true);
+          mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, 1, false);
           umma_commit(slab01_free);                     // the half-0 epilogue may now overwrite slabs 0,1
-          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, two, 1, false);
-          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, two, 1, false);
+          mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, 1, false);
+          mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, 1, false);
           umma_commit(&acc_full[1]);
+          stamp(u, 1, 1);
         }
         if (kOut) {
           // ---- output layer: N = 16 (rows 0..7 hi, 8..15 lo halves of the <= 4 real output rows), accumulators in acc[.][1]
@@ -217,7 +248,8 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
           mbar_wait(&w_full[s], ph);
           tc_fence_after();
-          for (int t = 0; t < (two ? 2 : 1); ++t)
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = smem_desc_sw128(s_act + (t * 4 + k) * kChSlab, 16, 1024);
@@ -240,7 +272,12 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
     uint32_t c_acc0 = 0, c_acc1 = 0, c_free = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int it_no = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_no) {
+      const bool tr = jobs.trace && blockIdx.x == 0 && it_no < 2 && (threadIdx.x == 64 || threadIdx.x == 192);
+      auto stamp = [&](int u, int h, int e) {
+        if (tr) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 4 + grp * 6 + e] = clock64();
+      };
       const ChainJob& J = jobs.c[item / n_pairs];
       const int tile = 2 * (item % n_pairs) + grp;
       const bool valid = tile < jobs.n_tiles;
@@ -254,6 +291,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           mbar_wait(&acc_full[h], (h ? c_acc1 : c_acc0) & 1);
           if (h) ++c_acc1; else ++c_acc0;
           tc_fence_after();
+          stamp(u, h, 0);
           if (valid) {
             // the TMA stores that read slabs 2h, 2h+1 (this group's second-newest commit group) must have finished reading
             if (gleader) bulk_wait_read<1>();
@@ -263,6 +301,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
             mbar_wait(slab01_free, c_free & 1);
             ++c_free;
           }
+          stamp(u, h, 1);
           if (valid) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -277,14 +316,15 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
               const uint32_t ob = s_act + (uint32_t)(grp * 4 + j) * kChSlab + sw_row;
               uint32_t obits[2] = {0u, 0u};
               const uint32_t mw[2] = {jj == 0 ? mb.x : mb.z, jj == 0 ? mb.y : mb.w};
-              const float4* bp = reinterpret_cast<const float4*>(U.bias + j * 64);
+              const uint32_t bp = smem_u32(smem + kChBiasOff) + (uint32_t)(((item / n_pairs) * kChUnits + u) * 256 + j * 64) * 4;
               tmem_ld_wait();
+              stamp(u, h, 2 + jj);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 uint32_t w[4];
                 float bv[8];
                 if (MODE == CH_FWD) {
-                  const float4 b0 = __ldg(bp + 2 * i), b1 = __ldg(bp + 2 * i + 1);
+                  const float4 b0 = lds128f(bp + i * 32), b1 = lds128f(bp + i * 32 + 16);
                   bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
                 }
 #pragma unroll
@@ -312,6 +352,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
             }
             fence_proxy_async_smem();
           }
+          stamp(u, h, 4);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&epi_done[h]);        // the MMA warp may read the slabs / overwrite the accumulators
@@ -323,6 +364,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
               bulk_commit();
             }
           }
+          stamp(u, h, 5);
         }
       }
       if (kOut) {

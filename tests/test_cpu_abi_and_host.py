@@ -152,3 +152,19 @@ def test_attrdict():
     assert d.pop("a") == 1 and "a" not in d
     with pytest.raises(AttributeError):
         d.missing
+
+
+def test_no_predicated_tensor_core_mma_in_sass():
+    """ptxas 12.9 if-converts a branch around tcgen05.mma into a predicated UTCHMMA whose descriptor moves (R2UR) can end
+    up guarded by an unrelated predicate: the MMA then runs with stale descriptors (seen in k_tc_chain).  Every tcgen05.mma
+    of the library must therefore be issued unconditionally; this scans the built SASS for a predicated one."""
+    import shutil
+    import subprocess
+    from marf_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    lib = build.build()
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    lines = [l for l in sass.splitlines() if "UTCHMMA" in l]
+    assert len(lines) > 50, "tensor-core MMAs missing from the library?"
+    bad = [l.strip() for l in lines if "@" in l.split("UTCHMMA")[0]]
+    assert not bad, bad[:4]
