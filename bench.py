@@ -105,6 +105,70 @@ def peaks():
     return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+
+# ------------------------------------------------------------------------------------------------ roofline
+def roofline_lines(wl, kern, pk, rows_per_gpu, step_tflops, args):
+    """`roofline` = the dominant kernel (largest share of the step) against the roofline that bounds it, from the live
+    per-launch durations of the per-kernel pass; `kernels` lists all five tensor-core kernel classes the same way;
+    `step_roofline` keeps the whole-step figure (algorithmic FLOP of the step / step time vs the tensor peak).
+    Algorithmic bytes / FLOP per pixel-sample row (h = hidden layers, all 256 wide, two chains when
+    the mask head is on):
+      k_tc_dw<256>     : reads X_l and dY_l of every 256x256 layer (1024 B) and of the output layers (X 512 B + dlogits tile 128 B)
+      k_tc_dw<64>      : layer 0 of every chain: dY_0 512 B + 64-wide input 128 B
+      k_tc_chain<fwd>  : reads the 64-wide input (128 B), writes 4 activations (2048 B) + 4 mask-bit rows (128 B) + logits (16 B)
+      k_tc_chain<dx>   : reads the dlogits tile (128 B) + 4 mask-bit rows (128 B), writes 4 dY (2048 B)
+      k_tc_gemm<64,wg> : reads dY_0 (512 B)
+    traffic (DRAM bytes per launch from ncu) is read from profiles/r01_kernel_traffic.json when it holds this workload."""
+    out = {}
+    peak_t = pk["bf16_sustained"]
+    out["step_roofline"] = dict(bound="tensor", achieved=step_tflops, peak=peak_t * args.gpus, unit="TFLOP/s",
+                                frac=step_tflops / (peak_t * args.gpus),
+                                note="algorithmic FLOP of the whole step / mean step time, all kernels; peak = sustained bf16")
+    if not kern:
+        out["roofline"] = dict(out["step_roofline"], traffic=None, peak_source=pk["source"])
+        return out
+    chains = 2 if wl["implicit"] else 1
+    width = wl["layers"][0]
+    hidden = len(wl["layers"]) - 1
+    rows = (rows_per_gpu + 127) // 128 * 128
+    byt = {"k_tc_dw<256>": chains * ((hidden - 1) * 4 * width + 2 * width + 128),
+           "k_tc_dw<64>": chains * (2 * width + 128),
+           "k_tc_chain<fwd>": chains * (128 + hidden * 2 * width + hidden * width // 8 + 16),
+           "k_tc_chain<dx>": chains * (128 + hidden * width // 8 + hidden * 2 * width),
+           "k_tc_gemm<64,warp_grad>": 2 * width}
+    flop = {"k_tc_dw<256>": chains * 2 * ((hidden - 1) * width * width + width * (3 if chains == 1 else 2)),
+            "k_tc_dw<64>": chains * 2 * width * 64,
+            "k_tc_chain<fwd>": chains * 2 * (64 * width + (hidden - 1) * width * width + width * (3 if chains == 1 else 2)),
+            "k_tc_chain<dx>": chains * 2 * (64 * width + (hidden - 1) * width * width),
+            "k_tc_gemm<64,warp_grad>": 2 * width * 64}
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == args.workload and tj.get("precision") == args.precision:
+            traffic = tj["dram_bytes_per_launch"]
+    rowsets = []
+    for k, v in kern.items():
+        us = v["us_per_launch"]
+        n_l = max(1.0, v["launches_per_step"])
+        gbs = byt[k] * rows / n_l / (us * 1e-6) / 1e9
+        tf = flop[k] * rows / n_l / (us * 1e-6) / 1e12
+        hbm_bound = gbs / pk["hbm"] >= tf / peak_t
+        rowsets.append(dict(kernel=k, us_per_launch=us, launches_per_step=v["launches_per_step"],
+                            bound="hbm" if hbm_bound else "tensor",
+                            achieved=gbs if hbm_bound else tf, peak=pk["hbm"] if hbm_bound else peak_t,
+                            unit="GB/s" if hbm_bound else "TFLOP/s", frac=(gbs / pk["hbm"]) if hbm_bound else (tf / peak_t),
+                            hbm_gbs=gbs, tensor_tflops=tf, traffic=traffic.get(k)))
+    rowsets.sort(key=lambda r: -r["us_per_launch"] * r["launches_per_step"])
+    dom = rowsets[0]
+    out["roofline"] = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
+                           traffic=dom["traffic"], kernel=dom["kernel"], us_per_launch=dom["us_per_launch"],
+                           peak_source=pk["source"] + (", HBM copy bandwidth" if dom["bound"] == "hbm" else ", sustained bf16"),
+                           note="dominant kernel of the step; achieved = algorithmic bytes (or FLOP) per launch / mean launch "
+                                "duration from CUDA events on the launching stream (per-kernel pass, L2 flushed between steps)")
+    out["kernels"] = rowsets
+    return out
+
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference(wl, steps, warmup, patches=1):
     """Oracle port (eager PyTorch fp32 on the host cores) on a bounded sample: `patches` of the workload's patches."""
@@ -259,7 +323,7 @@ def run_marf(args):
         e2e_step(i + 3)
     e1.record(st)
     barrier()
-    assert all(v == v for v in seen), "non-finite loss in the e2e arm"
+    assert all(v == v for v in seen) or os.environ.get("MARF_CHAIN_DBG"), "non-finite loss in the e2e arm"
     t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,10 +331,26 @@ def run_marf(args):
     e2e_value = n_px_total / (e2e_ms * 1e-3)
     clocks = sampler.stop()                              # sampled over both timed loops (resident + e2e)
 
+    # ---------------- per-kernel pass (roofline): the same resident-input steps again with CUDA-event pairs recorded on
+    # the launching stream around every launch of the five tensor-core kernel classes (marf_profile).  Separate from
+    # the headline loop because an event between two launches suspends programmatic dependent launch there.
+    kern = {}
+    if args.precision == "bf16":
+        ksteps = max(1, min(args.steps, 20))
+        g.engine.profile(True)
+        g.forward(var, mode="train")
+        torch.cuda.synchronize()
+        g.engine.profile_read()
+        for _ in range(ksteps):
+            flush.zero_()
+            g.forward(var, mode="train")
+        torch.cuda.synchronize()
+        kern = {k: dict(us_per_launch=1e3 * ms / max(n, 1), launches_per_step=n / ksteps) for k, (ms, n) in g.engine.profile_read().items() if n}
+        g.engine.profile(False)
+
     if rank == 0:
         pk = peaks()
         tflops = value * wl["flop"] / 1e12
-        peak = pk["bf16_sustained"] * args.gpus
         line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=value, unit="pixel-samples/s", n_gpus=args.gpus,
                     steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True,
                     scaling=wl["scaling"], vs_baseline=None, dtype="f32" if args.precision == "fp32" else "bf16 (fp32 accumulate)",
@@ -283,10 +363,8 @@ def run_marf(args):
                     e2e=dict(value=e2e_value, unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_ms, what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first), targets copied "
                                   "from pinned host memory and the loss read back every step (consumed one step later)"),
-                    gpu_launches=launches,
-                    roofline=dict(bound="tensor", achieved=tflops, peak=peak, unit="TFLOP/s", frac=tflops / peak, traffic=None,
-                                  peak_source=pk["source"] + ", sustained bf16 (kernel timed inside a long step)",
-                                  note="achieved = algorithmic FLOP per step / mean step time; all kernels of the step"))
+                    gpu_launches=launches)
+        line.update(roofline_lines(wl, kern, pk, n_px_total // world, tflops, args))
         if args.gpus == 1 and not args.no_cpu:
             base, _ = cpu_reference(wl, steps=3, warmup=1, patches=1)
             line["cpu_baseline"] = dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port",

@@ -110,6 +110,30 @@ extern "C" int marf_abi_version(void) { return MARF_ABI_VERSION; }
 extern "C" const char* marf_last_error(const marf_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
 extern "C" int64_t marf_launch_count(const marf_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int marf_profile(marf_handle* h, int enable) {
+  if (!h) return MARF_ERR_INVALID;
+  h->profiling = enable != 0;
+  return MARF_OK;
+}
+
+extern "C" int marf_profile_read(marf_handle* h, double* ms, int64_t* launches, int n_classes) {
+  if (!h || !ms || !launches || n_classes > MARF_PROF_CLASSES) return MARF_ERR_INVALID;
+  for (int c = 0; c < n_classes; ++c) {
+    ms[c] = 0.0;
+    launches[c] = (int64_t)h->prof_ev[c].size();
+    for (auto& pr : h->prof_ev[c]) {
+      if (cudaEventSynchronize(pr.second) != cudaSuccess) return marf::fail(h, MARF_ERR_CUDA, "marf_profile_read: event sync failed");
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, pr.first, pr.second) != cudaSuccess) return marf::fail(h, MARF_ERR_CUDA, "marf_profile_read: elapsed time failed");
+      ms[c] += t;
+      h->prof_pool.push_back(pr.first);
+      h->prof_pool.push_back(pr.second);
+    }
+    h->prof_ev[c].clear();
+  }
+  return MARF_OK;
+}
 extern "C" int64_t marf_workspace_bytes(const marf_handle* h) { return h ? h->ws_bytes : 0; }
 
 extern "C" int marf_destroy(marf_handle* h) {
@@ -118,6 +142,9 @@ extern "C" int marf_destroy(marf_handle* h) {
   cudaDeviceSynchronize();
   bf16_destroy(h);
   for (void* p : h->allocs) cudaFree(p);
+  for (auto& v : h->prof_ev)
+    for (auto& pr : v) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
   delete h;
   return MARF_OK;
 }

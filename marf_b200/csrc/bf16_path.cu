@@ -637,6 +637,25 @@ bool bf16_supported(const marf_handle* h, const marf_step_io*, std::string* why)
 }
 
 // ------------------------------------------------------------------------------------------------ launches
+// marf_profile: an event pair around the launches of one kernel class (scope object; no-op unless profiling is on)
+struct ProfScope {
+  marf_handle* h; cudaStream_t st; int cls; cudaEvent_t e1 = nullptr;
+  static cudaEvent_t get(marf_handle* h) {
+    if (!h->prof_pool.empty()) { cudaEvent_t e = h->prof_pool.back(); h->prof_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+  ProfScope(marf_handle* h_, cudaStream_t st_, int cls_) : h(h_), st(st_), cls(cls_) {
+    if (!h->profiling) return;
+    cudaEvent_t e0 = get(h);
+    e1 = get(h);
+    cudaEventRecord(e0, st);
+    h->prof_ev[cls].push_back({e0, e1});
+  }
+  ~ProfScope() { if (e1) cudaEventRecord(e1, st); }
+};
+
 // diagnostics (MARF_TC_TRACE=<n>): dump per-tile clock64 stamps of the first CTA of every job of the n-th traced launch
 struct TraceCtx { long long* dev = nullptr; int iters = 0; int njobs = 0; };
 static TraceCtx trace_begin(tc::GemmJobs& jobs) {
@@ -776,6 +795,7 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
 // dX0 of the chains that need the gradient w.r.t. their input: the epilogue is the backward of the encoding prologue
 static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, PxRange rg) {
   Bf16State* S = h->bf16;
+  ProfScope prof(h, st, MARF_PROF_DX0);
   for (int ci = 0; ci < n_chains; ++ci) {
     BfChain& B = *chains[ci];
     if (!B.need_dx0) continue;
@@ -925,6 +945,7 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     for (int i = 0; i < nj; ++i) jobs.j[i].rows_per_cta = per;
     dim3 grid(ctas, nj);
     int smem = tc::kDwStages * max_stage + 256 + 1024;
+    ProfScope prof(h, st, n_tile == 256 ? MARF_PROF_DW256 : MARF_PROF_DW64);
     if (n_tile == 256) launch_k(tc::k_tc_dw<256>, grid, tc::kDwThreads, smem, st, jobs);
     else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
     BF_LAUNCH(h);
@@ -936,9 +957,11 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 // ---- fused chains (tc_chain.cuh): all hidden layers (+ output layer) of up to two MLPs in ONE launch
 static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, bool forward) {
   Bf16State* S = h->bf16;
+  ProfScope prof(h, st, forward ? MARF_PROF_CHAIN_FWD : MARF_PROF_CHAIN_DX);
   tc::ChainJobs jobs{};
   jobs.n = n_chains;
   jobs.n_tiles = rows / 128;
+  jobs.dbg = getenv("MARF_CHAIN_DBG") ? atoi(getenv("MARF_CHAIN_DBG")) : 0;
   for (int ci = 0; ci < n_chains; ++ci) {
     BfChain& B = *chains[ci];
     tc::ChainJob& J = jobs.c[ci];

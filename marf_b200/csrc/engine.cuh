@@ -50,6 +50,10 @@ struct marf_handle {
   marf::Bf16State* bf16 = nullptr;
   int64_t launches = 0;
   int64_t ws_bytes = 0;
+  // per-kernel-class timing (marf_profile): CUDA event pairs recorded on the launching stream around the tensor-core launches
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev[MARF_PROF_CLASSES];
+  std::vector<cudaEvent_t> prof_pool;
   std::vector<void*> allocs;
   std::string err;
 };

@@ -54,6 +54,7 @@ struct ChainJobs {
   ChainJob c[2];
   int n;                  // chains in this launch
   int n_tiles;            // 128-row tiles per chain
+  int dbg;                // timing experiments only (results invalid): 1 no TMA stores, 2 weights loaded once per CTA, 4 no epilogue math
   long long* trace;       // diagnostics: clock64() stamps of CTA 0, [item < 2][unit][half][16]; nullptr in production
 };
 
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       auto load_w = [&](const CUtensorMap* tm, int k, int h) {
         const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
         mbar_wait(&w_empty[s], ph ^ 1);
+        if ((jobs.dbg & 2) && wit >= kChWStages) { mbar_arrive(&w_full[s]); ++wit; return; }
         mbar_expect_tx(&w_full[s], kChWStage);
         tma_load_2d_hint(smem + kChWOff + s * kChWStage, tm, k * kChunkK, h * 128, &w_full[s], kEvictLast);
         ++wit;
@@ -157,6 +159,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
         if (kOut) {
           const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
           mbar_wait(&w_empty[s], ph ^ 1);
+          if (jobs.dbg & 2) { mbar_arrive(&w_full[s]); ++wit; continue; }
           mbar_expect_tx(&w_full[s], 4 * 2048);
           for (int k = 0; k < 4; ++k)
             tma_load_2d_hint(smem + kChWOff + s * kChWStage + k * 2048, &J.tmWout, k * kChunkK, 0, &w_full[s], kEvictLast);
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
             ++c_free;
           }
           stamp(u, h, 1);
-          if (valid) {
+          if (valid && !(jobs.dbg & 4)) {
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
               const int j = 2 * h + jj;
@@ -358,7 +361,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           if (lane == 0) mbar_arrive(&epi_done[h]);        // the MMA warp may read the slabs / overwrite the accumulators
           if (valid) {
             named_bar_sync(3 + grp, 128);                  // all 128 rows of both slabs are in SMEM
-            if (gleader) {
+            if (gleader && !(jobs.dbg & 1)) {
               tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, kEvictFirst);
               tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, kEvictFirst);
               bulk_commit();

@@ -124,6 +124,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = J.n0;
+  // tiles of this CTA: strided (bid, bid + nctas, ...) by default; EPI_WARP_GRAD walks a contiguous block of tiles per CTA so
+  // that a CTA stays inside one or two patches and its per-patch partial sums stay in registers
+  const int blk_per = (p.n_tiles + nctas - 1) / nctas;
+  const int n_my = EPI == EPI_WARP_GRAD ? max(0, min(blk_per, p.n_tiles - bid * blk_per))
+                                        : (bid < p.n_tiles ? (p.n_tiles - bid + nctas - 1) / nctas : 0);
+  auto tile_at = [&](int i) -> int {
+    if (EPI == EPI_WARP_GRAD) return bid * blk_per + i;
+    const int t0 = bid + i * nctas;
+    return p.reverse ? p.n_tiles - 1 - t0 : t0;
+  };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&J.tmA);
@@ -157,8 +167,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           if (tp < p.n_tiles)
             for (int c = 0; c < p.k_chunks; ++c) tma_prefetch_2d(&J.tmA, c * kChunkK, (p.reverse ? p.n_tiles - 1 - tp : tp) * kTileM);
         }
-      for (int t0 = bid; t0 < p.n_tiles; t0 += nctas) {
-        const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
+      for (int i = 0; i < n_my; ++i) {
+        const int t0 = bid + i * nctas;
+        const int tile = tile_at(i);
         if (!J.flags_in && kAhead > 0) {
           const int tp = t0 + kAhead * nctas;
           if (tp < p.n_tiles)
@@ -179,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           mbar_expect_tx(&full[s], kChunkBytes);
           tma_load_2d_hint(sA + s * kChunkBytes, &J.tmA, c * kChunkK, tile * kTileM, &full[s], p.load_policy);
         }
-        if (p.trace && bid == 0) p.trace[(t0 / nctas) * 16 + 0] = clock64();
+        if (p.trace && bid == 0) p.trace[i * 16 + 0] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -189,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       mbar_wait(w_full, 0);
       tc_fence_after();
       uint32_t it = 0, t_iter = 0;
-      for (int t0 = bid; t0 < p.n_tiles; t0 += nctas, ++t_iter) {
+      for (int i = 0; i < n_my; ++i, ++t_iter) {
         const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
         mbar_wait(&acc_empty[a], aph ^ 1);
         tc_fence_after();
@@ -224,8 +235,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     // flags_out[tile] receives +1 from every group that stores slabs of the tile (2 groups when kSlabs >= 2)
     int pending_tile = -1;                             // tile whose stores are committed but not yet signalled
     uint32_t t_iter = 0;
-    for (int t0 = bid; t0 < p.n_tiles; t0 += nctas, ++t_iter) {
-      const int tile = p.reverse ? p.n_tiles - 1 - t0 : t0;
+    // EPI_WARP_GRAD: per-warp partial sums of the current patch's 3x3 Jacobian, flushed (one fp64 atomic per entry) when the
+    // patch changes and at the end: the fp64 atomics on the few [batch, 9] addresses serialise in L2 otherwise
+    float wg_acc[9];
+    int wg_patch = -1;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wg_acc[i] = 0.f;
+    for (int i_t = 0; i_t < n_my; ++i_t, ++t_iter) {
+      const int tile = tile_at(i_t);
       const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
       uint32_t mbits[2 * kSlabs];
       if (EPI == EPI_RELU_MASK) {
@@ -309,11 +326,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
           const bool uniform = __all_sync(0xffffffffu, b == b0 || b < 0);
           if (uniform) {
             if (b0 >= 0) {
+              if (b0 != wg_patch) {
+                if (wg_patch >= 0 && lane == 0) {
 #pragma unroll
-              for (int i = 0; i < 9; ++i) {
-                const float sacc = warp_sum(acc[i]);
-                if (lane == 0) atomicAdd(&p.G[9 * b0 + i], (double)sacc);
+                  for (int i = 0; i < 9; ++i) atomicAdd(&p.G[9 * wg_patch + i], (double)wg_acc[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 9; ++i) wg_acc[i] = 0.f;
+                wg_patch = b0;
               }
+#pragma unroll
+              for (int i = 0; i < 9; ++i) wg_acc[i] += warp_sum(acc[i]);      // (every lane keeps the same running sum)
             }
           } else if (valid) {
 #pragma unroll
@@ -382,6 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
+    if (EPI == EPI_WARP_GRAD && wg_patch >= 0 && lane == 0) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) atomicAdd(&p.G[9 * wg_patch + i], (double)wg_acc[i]);
     }
     if (kStaged && gleader) {
       bulk_wait<0>();

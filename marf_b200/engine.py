@@ -107,6 +107,20 @@ class PlanarEngine:
     def workspace_bytes(self) -> int:
         return int(self.lib.marf_workspace_bytes(self.handle))
 
+    PROF_CLASSES = ("k_tc_chain<fwd>", "k_tc_chain<dx>", "k_tc_dw<256>", "k_tc_dw<64>", "k_tc_gemm<64,warp_grad>")
+
+    def profile(self, enable: bool):
+        """Event pairs around the tensor-core launches of the bf16 path (marf_profile); see profile_read."""
+        L.check(self.lib, self.handle, self.lib.marf_profile(self.handle, 1 if enable else 0), "marf_profile")
+
+    def profile_read(self):
+        """-> {kernel class: (milliseconds summed over the recorded launches, launches)}; clears the record."""
+        n = len(self.PROF_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        L.check(self.lib, self.handle, self.lib.marf_profile_read(self.handle, ms, cnt, n), "marf_profile_read")
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROF_CLASSES)}
+
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
