@@ -590,8 +590,7 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
@@ -815,7 +814,6 @@ static int launch_dx0(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
     J.p.rg = rg;
     J.p.Hm = h->Hm;
     J.p.G = h->G;
-    J.p.wg_split = getenv("MARF_WG_SPLIT") ? 1 : 0;       // measured: one group doing both halves is faster
     J.cta_begin = 0;
     J.cta_count = std::min(J.p.n_tiles, S->num_sms);
     int smem = tc::gemm_smem(64, J.p.k_chunks, false).total + 1024;
@@ -879,80 +877,71 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
   return launch_dx0(h, st, chains, n_chains, rows, rg);
 }
 
-// all dW / db of the tensor-core layers of the given chains: one launch per N-tile width
+// all dW / db of the tensor-core layers of the given chains in ONE launch; the CTAs are split over the jobs by the bytes
+// each job streams
 static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, long long row_first) {
   Bf16State* S = h->bf16;
   (void)row_first;
-  for (int pass = 0; pass < 2; ++pass) {          // pass 0: N_TILE=256 jobs, pass 1: N_TILE=64 jobs
-    const int n_tile = pass == 0 ? 256 : 64;
-    tc::DwJobs jobs{};
-    int nj = 0;
-    int max_stage = 0;
-    for (int ci = 0; ci < n_chains; ++ci) {
-      BfChain& B = *chains[ci];
-      Chain& F = *B.f32;
-      if (pass == 0 && B.L[B.n - 1].k_in == 256) {
-        // output layer (3-/1-wide): dW = dlogits^T X_last through the same kernel (dlogits as a zero-padded bf16 tile)
-        if (nj >= tc::kDwMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
-        const int l = B.n - 1;
-        tc::DwJob& J = jobs.j[nj++];
-        J.tmDY = B.tmDL64;
-        J.tmX = B.tmAct64[l];
-        J.rows = rows;
-        J.m_halves = 1;
-        J.m_valid = B.L[l].k_out;
-        J.n_valid = B.L[l].k_in;
-        J.n0 = 0;
-        J.ld_w = F.ld_in[l];
-        J.do_bias = 1;
-        J.dW = F.gWp[l];
-        J.db = F.gbp[l];
-        max_stage = std::max(max_stage, (2 + 256 / 64) * tc::kDwSlab);
-      }
-      for (int l = 0; l < B.n - 1; ++l) {
-        BfLayer& L = B.L[l];
-        const int lt = L.kp >= 256 ? 256 : 64;
-        if (lt == 64 && L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: input width must be 64 or >= 256");
-        if (lt != n_tile) continue;
-        const int n_tiles_n = (L.kp + n_tile - 1) / n_tile;
-        for (int t = 0; t < n_tiles_n; ++t) {
-          if (nj >= tc::kDwMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
-          tc::DwJob& J = jobs.j[nj++];
-          J.tmDY = B.tmDY64[l];
-          J.tmX = B.tmAct64[l];
-          J.rows = rows;
-          J.m_halves = (L.k_out + 127) / 128;
-          J.m_valid = L.k_out;
-          J.n_valid = L.k_in;
-          J.n0 = t * n_tile;
-          J.ld_w = F.ld_in[l];
-          J.do_bias = t == 0;
-          J.dW = F.gWp[l];
-          J.db = F.gbp[l];
-          if (l == 0 && B.col_off0 > 0) {
-            // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
-            // k_mask_dw_finalize turns into dW0 / db0
-            J.dW = B.dW0x; J.ld_w = 64; J.n_valid = 64; J.do_bias = 0;
-          }
-          max_stage = std::max(max_stage, (J.m_halves * 2 + n_tile / 64) * tc::kDwSlab);
-        }
+  tc::DwJobs jobs{};
+  int nj = 0;
+  int weight[tc::kDwMaxJobs];
+  auto add = [&](const CUtensorMap& tmDY, const CUtensorMap& tmX, int n_tile, int m_valid, int n_valid, int n0, int ld_w, int do_bias,
+                 float* dW, float* db) -> bool {
+    if (nj >= tc::kDwMaxJobs) return false;
+    tc::DwJob& J = jobs.j[nj];
+    J.tmDY = tmDY; J.tmX = tmX; J.rows = rows; J.n_tile = n_tile; J.m_halves = (m_valid + 127) / 128; J.m_valid = m_valid;
+    J.n_valid = n_valid; J.n0 = n0; J.ld_w = ld_w; J.do_bias = do_bias; J.dW = dW; J.db = db;
+    weight[nj++] = J.m_halves * 128 + n_tile;            // bytes per pixel row ~ (dY columns + X columns)
+    return true;
+  };
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    Chain& F = *B.f32;
+    if (B.L[B.n - 1].k_in == 256) {
+      // output layer (3-/1-wide): dW = dlogits^T X_last through the same kernel (dlogits as a zero-padded bf16 tile)
+      const int l = B.n - 1;
+      if (!add(B.tmDL64, B.tmAct64[l], 256, B.L[l].k_out, B.L[l].k_in, 0, F.ld_in[l], 1, F.gWp[l], F.gbp[l]))
+        return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
+    }
+    for (int l = 0; l < B.n - 1; ++l) {
+      BfLayer& L = B.L[l];
+      const int n_tile = L.kp >= 256 ? 256 : 64;
+      if (n_tile == 64 && L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: input width must be 64 or >= 256");
+      const int n_tiles_n = (L.kp + n_tile - 1) / n_tile;
+      for (int t = 0; t < n_tiles_n; ++t) {
+        bool ok;
+        if (l == 0 && B.col_off0 > 0)
+          // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
+          // k_mask_dw_finalize turns into dW0 / db0
+          ok = add(B.tmDY64[l], B.tmAct64[l], n_tile, L.k_out, 64, t * n_tile, 64, 0, B.dW0x, F.gbp[l]);
+        else
+          ok = add(B.tmDY64[l], B.tmAct64[l], n_tile, L.k_out, L.k_in, t * n_tile, F.ld_in[l], t == 0, F.gWp[l], F.gbp[l]);
+        if (!ok) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
       }
     }
-    if (nj == 0) continue;
-    int ctas = std::max(1, S->num_sms / nj);
-    int per = std::max((int)round_up((rows + ctas - 1) / ctas, 64), 64);
-    ctas = (rows + per - 1) / per;
-    for (int i = 0; i < nj; ++i) jobs.j[i].rows_per_cta = per;
-    dim3 grid(ctas, nj);
-    int smem = tc::kDwStages * max_stage + 256 + 1024;
-    ProfScope prof(h, st, n_tile == 256 ? MARF_PROF_DW256 : MARF_PROF_DW64);
-    if (n_tile == 256) launch_k(tc::k_tc_dw<256>, grid, tc::kDwThreads, smem, st, jobs);
-    else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
-    BF_LAUNCH(h);
   }
+  if (nj == 0) return MARF_OK;
+  jobs.n = nj;
+  int wsum = 0;
+  for (int i = 0; i < nj; ++i) wsum += weight[i];
+  int begin = 0, left = S->num_sms;
+  for (int i = 0; i < nj; ++i) {
+    int c = std::max(1, (int)((long long)S->num_sms * weight[i] / wsum));
+    c = std::max(1, std::min(c, left - (nj - 1 - i)));
+    int per = std::max((int)round_up((rows + c - 1) / c, 64), 64);
+    c = (rows + per - 1) / per;
+    jobs.j[i].rows_per_cta = per;
+    jobs.j[i].cta_begin = begin;
+    jobs.j[i].cta_count = c;
+    begin += c;
+    left -= c;
+  }
+  const int smem = tc::kDwStages * 8 * tc::kDwSlab + 256 + 1024;
+  ProfScope prof(h, st, MARF_PROF_DW);
+  launch_k(tc::k_tc_dw, begin, tc::kDwThreads, smem, st, jobs);
+  BF_LAUNCH(h);
   return MARF_OK;
 }
-
 
 // ---- fused chains (tc_chain.cuh): all hidden layers (+ output layer) of up to two MLPs in ONE launch
 static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, bool forward) {
@@ -1370,8 +1359,7 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
   cudaFuncSetAttribute(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_PLAIN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(tc::k_tc_dw<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-  cudaFuncSetAttribute(tc::k_tc_dw<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  cudaFuncSetAttribute(tc::k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
   auto to_bf = [&](const float* src, int r, int c) -> bf16* {
     bf16* d = nullptr;
     if (cudaMalloc(&d, (size_t)r * c * 2) != cudaSuccess) return nullptr;
@@ -1481,18 +1469,15 @@ extern "C" int marf_tc_selftest(int device, int mode, int rows, int K, int N, co
     // out holds [N, K] weights followed by [N] bias sums
     cudaMemsetAsync(out, 0, ((size_t)N * K + N) * sizeof(float), st);
     tc::DwJobs jobs{};
+    jobs.n = n_tiles_n;
     for (int t = 0; t < n_tiles_n; ++t) {
       tc::DwJob& J = jobs.j[t];
-      J.tmDY = tA; J.tmX = tM; J.rows = rows; J.rows_per_cta = per; J.m_halves = (N + 127) / 128; J.m_valid = N;
+      J.tmDY = tA; J.tmX = tM; J.rows = rows; J.rows_per_cta = per; J.cta_begin = t * ctas; J.cta_count = ctas; J.n_tile = n_tile;
+      J.m_halves = (N + 127) / 128; J.m_valid = N;
       J.n_valid = K; J.n0 = t * n_tile; J.ld_w = K; J.do_bias = t == 0; J.dW = out; J.db = out + (size_t)N * K;
     }
-    int stage = (((N + 127) / 128) * 2 + n_tile / 64) * tc::kDwSlab;
-    int smem = tc::kDwStages * stage + 256 + 1024;
-    dim3 grid(ctas, n_tiles_n);
-    if (!rc) {
-      if (n_tile == 256) launch_k(tc::k_tc_dw<256>, grid, tc::kDwThreads, smem, st, jobs);
-      else launch_k(tc::k_tc_dw<64>, grid, tc::kDwThreads, smem, st, jobs);
-    }
+    int smem = tc::kDwStages * 8 * tc::kDwSlab + 256 + 1024;
+    if (!rc) launch_k(tc::k_tc_dw, ctas * n_tiles_n, tc::kDwThreads, smem, st, jobs);
   } else {
     return MARF_ERR_INVALID;
   }

@@ -45,7 +45,6 @@ struct GemmParams {
   PxRange rg;
   const float* Hm;      // [batch_global, 9]
   double* G;            // [batch, 9]
-  int wg_split;         // 1: epilogue group 0 handles the u half of the encoding, group 1 the v half; 0: group 0 does both
   long long* trace;     // diagnostics: per-tile clock64() stamps of CTA 0 ([tile_iter][16]); nullptr in production
 };
 
@@ -141,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
     if (kStaged) prefetch_tmap(&J.tmOut);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(w_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    // (EPI_WARP_GRAD: the two epilogue groups take alternate tiles = alternate accumulators, 4 warps release each)
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI == EPI_WARP_GRAD ? 4 : 8); }
     fence_barrier_init();
     // the weights were packed at least two launches ago: fetch them while the previous kernel is still draining
     mbar_expect_tx(w_full, (uint32_t)L.w_bytes);
@@ -242,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
 #pragma unroll
     for (int i = 0; i < 9; ++i) wg_acc[i] = 0.f;
     for (int i_t = 0; i_t < n_my; ++i_t, ++t_iter) {
+      if (EPI == EPI_WARP_GRAD && (int)(t_iter & 1) != grp) continue;      // the other group's tile
       const int tile = tile_at(i_t);
       const uint32_t a = t_iter & 1, aph = (t_iter >> 1) & 1;
       uint32_t mbits[2 * kSlabs];
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
       if (tr) p.trace[t_iter * 16 + 3 + grp * 6] = clock64();
 #pragma unroll
       for (int j = 0; j < kSlabs; ++j) {
-        if ((EPI != EPI_WARP_GRAD || !p.wg_split) && (j & 1) != grp) continue;   // (split EPI_WARP_GRAD: both groups share slab 0)
+        if (EPI != EPI_WARP_GRAD && (j & 1) != grp) continue;
         uint32_t v[64];
         {
           uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
@@ -284,8 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_tc_gemm(const __grid_constant__
             float x, y, u, vv, qz;
             grid_xy(p.geo, rr, cc, x, y);
             apply_h(p.Hm + 9 * (b + p.geo.patch_offset), x, y, u, vv, qz);
-            // the two epilogue groups split the work: group 0 differentiates the u half of the encoding, group 1 the v half
-            const bool do_u = !p.wg_split || grp == 0, do_v = !p.wg_split || grp == 1;
+            const bool do_u = true, do_v = true;
             float gu = do_u ? __uint_as_float(v[0]) : 0.f, gv = do_v ? __uint_as_float(v[1]) : 0.f;
             const int Lb = LT > 0 ? LT : p.geo.L;
 #pragma unroll
@@ -434,6 +434,8 @@ struct DwJob {
   CUtensorMap tmX;      // box {64,64} over X  [rows, in]
   int rows;             // padded pixel rows (multiple of 64)
   int rows_per_cta;     // multiple of 64
+  int cta_begin, cta_count;   // CTAs [cta_begin, cta_begin + cta_count) of the launch split this job's pixel rows
+  int n_tile;           // input columns of this job's tile: 64 or 256 (the MMA N)
   int m_halves;         // ceil(out / 128)
   int m_valid;          // out features
   int n_valid;          // in features
@@ -444,31 +446,39 @@ struct DwJob {
   float* db;            // [out] fp32
 };
 constexpr int kDwMaxJobs = 12;
-struct DwJobs { DwJob j[kDwMaxJobs]; };
+struct DwJobs { DwJob j[kDwMaxJobs]; int n; };
 
 constexpr int kDwStages = 3;
 constexpr int kDwRows = 64;                 // pixel rows per stage
 constexpr int kDwSlab = kDwRows * 128;      // [64 rows x 64 cols] bf16
 
-template <int N_TILE>
+// One launch covers every layer of both networks ("jobs"); a contiguous range of CTAs splits the pixel rows of a job
+// (ranges sized by the bytes the job streams).  The tile width N (64 for the encoded-input layers, 256 otherwise) is a
+// per-job runtime value: it only enters the instruction descriptor, the stage layout and the epilogue bounds.
 __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__ DwJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const DwJob& J = jobs.j[blockIdx.y];
-  constexpr int kBSlabs = N_TILE / 64;
+  int jr = 0;
+  for (int i = 1; i < jobs.n; ++i)
+    if ((int)blockIdx.x >= jobs.j[i].cta_begin) jr = i;
+  const DwJob& J = jobs.j[jr];
+  const int bid = (int)blockIdx.x - J.cta_begin;
+  const int n_tile = J.n_tile;
+  const int b_slabs = n_tile / 64;
   const int a_slabs = J.m_halves * 2;
-  const int stage_bytes = (a_slabs + kBSlabs) * kDwSlab;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * stage_bytes);
+  const int stage_bytes = (a_slabs + b_slabs) * kDwSlab;
+  const int stage_stride = (4 + 4) * kDwSlab;                 // stages are laid out for the largest job
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kDwStages * stage_stride);
   uint64_t* full = bars;
   uint64_t* empty = bars + kDwStages;
   uint64_t* done = bars + 2 * kDwStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  const uint32_t tmem_cols = 512;   // m_halves * N_TILE <= 512
+  const uint32_t tmem_cols = 512;   // m_halves * n_tile <= 512
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_begin = blockIdx.x * J.rows_per_cta;
+  const int row_begin = bid * J.rows_per_cta;
   const int row_end = min(J.rows, row_begin + J.rows_per_cta);
-  const int n_iter = row_begin < row_end ? (row_end - row_begin) / kDwRows : 0;
+  const int n_iter = (bid < J.cta_count && row_begin < row_end) ? (row_end - row_begin) / kDwRows : 0;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&J.tmDY);
@@ -491,27 +501,30 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
           const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
-          uint8_t* st = smem + s * stage_bytes;
+          uint8_t* st = smem + s * stage_stride;
           const int row = row_begin + it * kDwRows;
           for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &J.tmDY, i * 64, row, &full[s]);
-          for (int i = 0; i < kBSlabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &J.tmX, J.n0 + i * 64, row, &full[s]);
+          for (int i = 0; i < b_slabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &J.tmX, J.n0 + i * 64, row, &full[s]);
         }
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = idesc_bf16(128, N_TILE, 1, 1);     // both operands MN-major
+        const uint32_t idesc = idesc_bf16(128, n_tile, 1, 1);     // both operands MN-major
         for (int it = 0; it < n_iter; ++it) {
           const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t st = smem_u32(smem + s * stage_bytes);
+          const uint32_t st = smem_u32(smem + s * stage_stride);
 #pragma unroll
           for (int ks = 0; ks < kDwRows / 16; ++ks) {
             const uint64_t db = smem_desc_sw128(st + a_slabs * kDwSlab + ks * 2048, kDwSlab, 1024);
-            for (int mh = 0; mh < J.m_halves; ++mh) {
-              const uint64_t da = smem_desc_sw128(st + mh * 2 * kDwSlab + ks * 2048, kDwSlab, 1024);
-              umma_bf16(tmem_base + mh * N_TILE, da, db, idesc, (it | ks) != 0);
-            }
+            // Both 128-row halves of dY^T unconditionally: for a one-half job (output layers) the second MMA multiplies
+            // whatever lies behind the two dY slabs into TMEM columns nobody reads.  A branch here would be if-converted
+            // by ptxas into a predicated UTCHMMA (see tc_chain.cuh) — every tcgen05.mma stays unconditional.
+            const uint64_t da0 = smem_desc_sw128(st + ks * 2048, kDwSlab, 1024);
+            const uint64_t da1 = smem_desc_sw128(st + 2 * kDwSlab + ks * 2048, kDwSlab, 1024);
+            umma_bf16(tmem_base, da0, db, idesc, (it | ks) != 0);
+            umma_bf16(tmem_base + n_tile, da1, db, idesc, (it | ks) != 0);
           }
           umma_commit(&empty[s]);
         }
@@ -527,11 +540,11 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
         const uint32_t s = it % kDwStages, ph = (it / kDwStages) & 1;
         mbar_wait(&full[s], ph);
         if (bias_warp) {
-          const uint8_t* slab = smem + s * stage_bytes + q * kDwSlab;
+          const uint32_t slab = smem_u32(smem + s * stage_stride + q * kDwSlab);
 #pragma unroll 8
           for (int k = 0; k < kDwRows; ++k) {
-            const uint32_t w = *reinterpret_cast<const uint32_t*>(slab + k * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)k & 7)) << 4) +
-                                                                  ((uint32_t)lane & 3) * 4);
+            uint32_t w;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(slab + k * 128 + ((((uint32_t)lane >> 2) ^ ((uint32_t)k & 7)) << 4) + ((uint32_t)lane & 3) * 4));
             bs0 += __uint_as_float(w << 16);
             bs1 += __uint_as_float(w & 0xFFFF0000u);
           }
@@ -550,9 +563,9 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
       for (int mh = 0; mh < J.m_halves; ++mh) {
         const int m = mh * 128 + r;
 #pragma unroll 1
-        for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+        for (int c0 = 0; c0 < n_tile; c0 += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * N_TILE + c0, v);
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * n_tile + c0, v);
           tmem_ld_wait();
           if (m < J.m_valid) {
             float* o = J.dW + (size_t)m * J.ld_w + J.n0 + c0;
