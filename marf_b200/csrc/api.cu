@@ -442,10 +442,10 @@ static int edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const marf_config& c = h->cfg;
   const float* pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
   double* ep = io->edge_pred ? io->edge_pred : h->edge_pred;
-  long long tot = h->n_local * 3;
-  launch_k(k_sobel_mag, (unsigned)((tot + 255) / 256), 256, 0, st, pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
+  const dim3 eg((unsigned)((c.rows * h->w + 255) / 256), (unsigned)(c.batch * 3));     // x: one plane, y: image * 3 + channel
+  launch_k(k_sobel_mag, eg, 256, 0, st, pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
   LAUNCH_CHECK(h);
-  launch_k(k_gauss5, (unsigned)((tot + 255) / 256), 256, 0, st, h->edge_mag, c.batch * 3, c.rows, h->w, ep);
+  launch_k(k_gauss5, eg, 256, 0, st, h->edge_mag, c.batch * 3, c.rows, h->w, ep);
   LAUNCH_CHECK(h);
   EdgeArgs e;
   e.mask_mode = c.mask_mode;
@@ -740,9 +740,11 @@ extern "C" int marf_compute_edges(marf_handle* h, const float* images, int32_t n
   long long tot = (long long)n * c * rows * w;
   double* mag = nullptr;
   CUDA_TRY(h, cudaMallocAsync((void**)&mag, tot * sizeof(double), st));
-  launch_k(k_sobel_mag, (unsigned)((tot + 255) / 256), 256, 0, st, images, n, c, rows, w, 0, mag);
+  if ((long long)n * c > 65535) return fail(h, MARF_ERR_INVALID, "marf_compute_edges: more than 65535 planes");
+  const dim3 eg((unsigned)((rows * w + 255) / 256), (unsigned)(n * c));
+  launch_k(k_sobel_mag, eg, 256, 0, st, images, n, c, rows, w, 0, mag);
   LAUNCH_CHECK(h);
-  launch_k(k_gauss5, (unsigned)((tot + 255) / 256), 256, 0, st, mag, n * c, rows, w, out);
+  launch_k(k_gauss5, eg, 256, 0, st, mag, n * c, rows, w, out);
   LAUNCH_CHECK(h);
   CUDA_TRY(h, cudaFreeAsync(mag, st));
   return MARF_OK;

@@ -922,19 +922,28 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
   }
   if (nj == 0) return MARF_OK;
   jobs.n = nj;
+  // CTAs per job proportional to the bytes it streams (largest-remainder rounding so that every SM gets a CTA)
   int wsum = 0;
   for (int i = 0; i < nj; ++i) wsum += weight[i];
-  int begin = 0, left = S->num_sms;
+  int cnt[tc::kDwMaxJobs], rem[tc::kDwMaxJobs], used = 0;
   for (int i = 0; i < nj; ++i) {
-    int c = std::max(1, (int)((long long)S->num_sms * weight[i] / wsum));
-    c = std::max(1, std::min(c, left - (nj - 1 - i)));
-    int per = std::max((int)round_up((rows + c - 1) / c, 64), 64);
-    c = (rows + per - 1) / per;
+    const long long x = (long long)S->num_sms * weight[i];
+    cnt[i] = std::max(1, (int)(x / wsum));
+    rem[i] = (int)(x % wsum);
+    used += cnt[i];
+  }
+  while (used < S->num_sms) {
+    int best = 0;
+    for (int i = 1; i < nj; ++i) if (rem[i] > rem[best]) best = i;
+    cnt[best]++; rem[best] = -1; used++;
+  }
+  int begin = 0;
+  for (int i = 0; i < nj; ++i) {
+    const int per = std::max((int)round_up((rows + cnt[i] - 1) / cnt[i], 64), 64);
     jobs.j[i].rows_per_cta = per;
     jobs.j[i].cta_begin = begin;
-    jobs.j[i].cta_count = c;
-    begin += c;
-    left -= c;
+    jobs.j[i].cta_count = (rows + per - 1) / per;          // (<= cnt[i]; trailing CTAs of the range would have no rows)
+    begin += jobs.j[i].cta_count;
   }
   const int smem = tc::kDwStages * 8 * tc::kDwSlab + 256 + 1024;
   ProfScope prof(h, st, MARF_PROF_DW);

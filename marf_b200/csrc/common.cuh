@@ -55,11 +55,19 @@ struct PxRange {
 };
 
 __device__ __forceinline__ void decode_px(const Geo& g, long long i, int& b, int& r, int& c) {
-  long long per = (long long)g.rows * g.w;
-  b = (int)(i / per);
-  int rem = (int)(i - (long long)b * per);
-  r = rem / g.w + g.row_offset;
-  c = rem - (rem / g.w) * g.w;
+  const long long per = (long long)g.rows * g.w;
+  int rem;
+  if (i < 0x7fffffffLL) {                     // (64-bit division is ~10x the cost of the 32-bit one; the branch is uniform)
+    const unsigned ui = (unsigned)i, up = (unsigned)per;
+    b = (int)(ui / up);
+    rem = (int)(ui - (unsigned)b * up);
+  } else {
+    b = (int)(i / per);
+    rem = (int)(i - (long long)b * per);
+  }
+  const int q = rem / g.w;
+  r = q + g.row_offset;
+  c = rem - q * g.w;
 }
 
 // Programmatic dependent launch: block until every kernel this launch depends on has completed and flushed.

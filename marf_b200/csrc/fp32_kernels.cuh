@@ -706,13 +706,13 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch, int rows, int w, int interleaved,
                             double* __restrict__ mag /* planar [n,ch,rows,w] */) {
   pdl_wait();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)n * ch * rows * w;
-  if (i >= total) return;
-  int x = (int)(i % w);
-  int y = (int)((i / w) % rows);
-  int c = (int)((i / ((long long)w * rows)) % ch);
-  int b = (int)(i / ((long long)w * rows * ch));
+  // grid: x covers one [rows, w] plane, y = plane (image * ch + channel): 32-bit index arithmetic only
+  const int pi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pi >= rows * w) return;
+  const int y = pi / w, x = pi - y * w;
+  const int c = (int)(blockIdx.y % (unsigned)ch), b = (int)(blockIdx.y / (unsigned)ch);
+  const long long i = (long long)blockIdx.y * rows * w + pi;
+  (void)n;
   auto px = [&](int yy, int xx) -> double {
     yy = reflect101(yy, rows); xx = reflect101(xx, w);
     return interleaved ? (double)img[(((long long)b * rows + yy) * w + xx) * ch + c]
@@ -733,12 +733,12 @@ static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch,
 
 static __global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
   pdl_wait();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)planes * rows * w;
-  if (i >= total) return;
-  int x = (int)(i % w);
-  int y = (int)((i / w) % rows);
-  long long p = i / ((long long)w * rows);
+  const int pi = blockIdx.x * blockDim.x + threadIdx.x;     // grid: x covers one plane, y = plane
+  if (pi >= rows * w) return;
+  const int y = pi / w, x = pi - y * w;
+  const long long p = blockIdx.y;
+  const long long i = p * rows * w + pi;
+  (void)planes;
   const double g5[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
   const double* pl = mag + p * rows * w;
   // separable, rows first then columns (same result as OpenCV's row/column filter order up to fp64 rounding)
