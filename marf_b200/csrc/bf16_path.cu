@@ -427,6 +427,7 @@ struct BfLayer {
   bf16* Wt = nullptr;    // [kp, np]   dX B operand (K-major over out features)
   CUtensorMap tmWk, tmWt;
   CUtensorMap tmWk128, tmWt128;   // 128-row boxes: the weight chunks of the fused chain kernel
+  CUtensorMap tmWk64, tmWt64;     // 64-row boxes: one CTA's half of a weight chunk (CTA-pair chain kernel)
 };
 
 struct BfChain {
@@ -446,9 +447,9 @@ struct BfChain {
   bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW / dX
   CUtensorMap tmDL64, tmDL128;
   bf16* Wlast_t = nullptr;                // [k_in(last), 64] bf16: W_last^T zero padded (B operand of the output layer's dX GEMM)
-  CUtensorMap tmWlast_t, tmWlast128;
+  CUtensorMap tmWlast_t, tmWlast128, tmWlast64;
   bf16* Wout16 = nullptr;                 // [16, k_in(last)] bf16: rows 0..7 hi, 8..15 lo halves of W_last (fused chain output layer)
-  CUtensorMap tmWout16;
+  CUtensorMap tmWout16, tmWout8;
   bool fused = false;                     // shape served by k_tc_chain: 64 -> 256 x4 -> (<=4)
   Chain* f32 = nullptr;                   // padded fp32 twin (gradient accumulators, bias)
   bool need_dx0 = false;
@@ -518,6 +519,10 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
       if (rc) return rc;
       rc = make_tmap(h, S, &L.tmWt128, L.Wt, L.kp, L.np, std::min(L.kp, 128));
       if (rc) return rc;
+      rc = make_tmap(h, S, &L.tmWk64, L.Wk, L.np, L.kp, 64);
+      if (rc) return rc;
+      rc = make_tmap(h, S, &L.tmWt64, L.Wt, L.kp, L.np, 64);
+      if (rc) return rc;
     } else if (l != F.n - 1) {
       return fail(h, MARF_ERR_UNSUPPORTED, "bf16: thin hidden layers are not supported");
     } else if (L.k_in != 256 && L.k_in != 512) {
@@ -572,6 +577,10 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     if (!B.Wout16) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (output layer)");
     rc = make_tmap(h, S, &B.tmWout16, B.Wout16, 16, kl, 16);
     if (rc) return rc;
+    rc = make_tmap(h, S, &B.tmWout8, B.Wout16, 16, kl, 8);
+    if (rc) return rc;
+    rc = make_tmap(h, S, &B.tmWlast64, B.Wlast_t, kl, 64, 64);
+    if (rc) return rc;
     bool ok = B.n - 1 == tc::kChUnits && B.L[0].kp == 64 && B.L[B.n - 1].k_out <= 4;
     for (int l = 0; l < B.n - 1; ++l) ok = ok && B.L[l].np == 256 && (l == 0 || B.L[l].kp == 256);
     B.fused = ok && getenv("MARF_NO_FUSE") == nullptr;
@@ -591,8 +600,10 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_gemm<64, tc::EPI_WARP_GRAD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1 * 512 + 1) * 4));
   return MARF_OK;
@@ -956,6 +967,9 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, bool forward) {
   Bf16State* S = h->bf16;
   ProfScope prof(h, st, forward ? MARF_PROF_CHAIN_FWD : MARF_PROF_CHAIN_DX);
+  // CTA pairs (cluster of 2, cta_group::2 MMAs) by default; MARF_CHAIN_CL=1 selects the single-CTA variant (tests, A/B runs)
+  const char* cl_env = getenv("MARF_CHAIN_CL");
+  const int cl = (cl_env && atoi(cl_env) == 1) || S->num_sms < 2 ? 1 : 2;
   tc::ChainJobs jobs{};
   jobs.n = n_chains;
   jobs.n_tiles = rows / 128;
@@ -967,9 +981,9 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
     J.bits_ld = 256 / 32;
     if (forward) {
       J.tmIn = B.tmAct128[0];
-      J.tmWout = B.tmWout16;
+      J.tmWout = cl == 2 ? B.tmWout8 : B.tmWout16;
       for (int u = 0; u < tc::kChUnits; ++u) {
-        J.u[u].tmW = B.L[u].tmWk128;
+        J.u[u].tmW = cl == 2 ? B.L[u].tmWk64 : B.L[u].tmWk128;
         J.u[u].tmOut = B.tmAct128[u + 1];
         J.u[u].bias = (u == 0 && B.col_off0 > 0) ? B.zero_bias : B.f32->bp[u];   // (class-table mode: b0 lives in Wk)
         J.u[u].bits = B.bits[u + 1];
@@ -983,15 +997,16 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
       J.tmWout = B.tmWout16;                 // unused
       for (int u = 0; u < tc::kChUnits; ++u) {
         const int l = n - 1 - u;
-        J.u[u].tmW = u == 0 ? B.tmWlast128 : B.L[l].tmWt128;
+        J.u[u].tmW = u == 0 ? (cl == 2 ? B.tmWlast64 : B.tmWlast128) : (cl == 2 ? B.L[l].tmWt64 : B.L[l].tmWt128);
         J.u[u].tmOut = B.tmDY128[l - 1];
         J.u[u].bias = nullptr;
         J.u[u].bits = B.bits[l];
       }
     }
   }
-  const int n_items = (jobs.n_tiles + 1) / 2 * n_chains;
-  const int grid = std::min(n_items, S->num_sms);
+  const int group = 2 * cl;
+  const int n_items = (jobs.n_tiles + group - 1) / group * n_chains;
+  const int grid = cl * std::min(n_items, S->num_sms / cl);
   const int smem = tc::kChSmem + 1024;
   // diagnostics (MARF_CHAIN_TRACE=<n>): clock64 stamps of CTA 0 during the n-th chain launch
   static int calls = 0;
@@ -1001,8 +1016,13 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
     cudaMalloc(&jobs.trace, 2 * 4 * 2 * 16 * sizeof(long long));
     cudaMemset(jobs.trace, 0, 2 * 4 * 2 * 16 * sizeof(long long));
   }
-  if (forward) launch_k(tc::k_tc_chain<tc::CH_FWD>, grid, tc::kChThreads, smem, st, jobs);
-  else launch_k(tc::k_tc_chain<tc::CH_DX>, grid, tc::kChThreads, smem, st, jobs);
+  if (cl == 2) {
+    if (forward) launch_k_cluster(tc::k_tc_chain<tc::CH_FWD, 2>, grid, tc::kChThreads, smem, st, 2, jobs);
+    else launch_k_cluster(tc::k_tc_chain<tc::CH_DX, 2>, grid, tc::kChThreads, smem, st, 2, jobs);
+  } else {
+    if (forward) launch_k(tc::k_tc_chain<tc::CH_FWD, 1>, grid, tc::kChThreads, smem, st, jobs);
+    else launch_k(tc::k_tc_chain<tc::CH_DX, 1>, grid, tc::kChThreads, smem, st, jobs);
+  }
   BF_LAUNCH(h);
   if (tracing) {
     cudaStreamSynchronize(st);

@@ -109,6 +109,26 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
   cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// the same with a thread-block cluster of `cluster` CTAs along x
+template <typename... KArgs, typename... Args>
+inline void launch_k_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int pad4(int a) { return (a + 3) / 4 * 4; }
 

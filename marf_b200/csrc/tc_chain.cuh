@@ -13,8 +13,9 @@
 // A layer is issued as two output halves h (128 columns each, accumulators acc[tile][h] = the 512 TMEM columns):
 // while the epilogue drains half h, the MMAs of the other half / of the next layer run.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
-// (group g = (warp-2)/4 owns tile g of the pair, warp%4 = TMEM lane quarter, thread = tile row).
+// Warp roles (352 threads): warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue
+// (group g = (warp-2)/4 owns tile g of the pair, warp%4 = TMEM lane quarter, thread = tile row), warp 10 = second MMA
+// issuer of the CTA-pair variant (idle otherwise).
 #pragma once
 #include "tc_kernels.cuh"
 
@@ -23,7 +24,7 @@ namespace tc {
 
 enum { CH_FWD = 0, CH_DX = 1 };
 
-constexpr int kChThreads = 320;
+constexpr int kChThreads = 352;
 constexpr int kChUnits = 4;                   // hidden units of a chain: 64 -> 256 -> 256 -> 256 -> 256
 constexpr int kChWStages = 3;
 constexpr int kChWStage = 128 * 128;          // [128 features x 64 K] bf16
@@ -76,7 +77,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-template <int MODE>
+// CL = 1: one CTA per tile pair.  CL = 2: a CTA pair (cluster of 2, cta_group::2): the two CTAs hold two tiles each, every
+// MMA covers 256 rows (tile t of both CTAs), each CTA loads and holds only HALF of every weight chunk (its 64 of the 128
+// output features), the leader CTA (cluster rank 0) issues all MMAs and its commits are multicast to both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's epi_done barriers.  Per tile-layer this takes a quarter of the SMEM
+// bandwidth off the MMA operand reads and halves the weight stream.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constant__ ChainJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -85,18 +91,25 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
   const uint32_t s_w = smem_u32(smem + kChWOff);
   const uint32_t s_in = smem_u32(smem + kChInOff);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChBarOff);
-  uint64_t* w_full = bars;                       // [4]
-  uint64_t* w_empty = bars + 4;                  // [4]
-  uint64_t* in_full = bars + 8;
-  uint64_t* in_empty = bars + 9;
-  uint64_t* acc_full = bars + 10;                // [2]  (per output half)
-  uint64_t* epi_done = bars + 12;                // [2]  (per output half): accumulators drained, output slabs written
-  uint64_t* slab01_free = bars + 14;             // the MMAs that read slabs 0,1 of the current layer input are complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  // weight ring: the 48 KB hold 3 whole chunks (CL = 1) or 6 half chunks (CL = 2: each CTA keeps only its 64 features)
+  constexpr int kStages = kChWStages * CL;
+  constexpr uint32_t kStageBytes = kChWStage / CL;
+  uint64_t* w_full = bars;                       // [<= 6]
+  uint64_t* w_empty = bars + 6;                  // [<= 6]
+  uint64_t* in_full = bars + 12;
+  uint64_t* in_empty = bars + 13;
+  uint64_t* acc_full = bars + 14;                // [2]  (per output half)
+  uint64_t* epi_done = bars + 16;                // [2]  (per output half): accumulators drained, output slabs written
+  uint64_t* slab01_free = bars + 18;             // the MMAs that read slabs 0,1 of the current layer input are complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_pairs = (jobs.n_tiles + 1) >> 1;
+  const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;      // work is distributed over clusters
+  constexpr int kGroup = 2 * CL;                                        // tiles per work item
+  const int n_pairs = (jobs.n_tiles + kGroup - 1) / kGroup;             // work items per chain
   const int n_items = n_pairs * jobs.n;
+  constexpr uint32_t kWBytes = kChWStage / CL;                          // this CTA's share of a weight chunk
 
   if (threadIdx.x == 0) {
     for (int c = 0; c < jobs.n; ++c) {
@@ -104,14 +117,18 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       for (int u = 0; u < kChUnits; ++u) { prefetch_tmap(&jobs.c[c].u[u].tmW); prefetch_tmap(&jobs.c[c].u[u].tmOut); }
       if (kOut) prefetch_tmap(&jobs.c[c].tmWout);
     }
-    for (int s = 0; s < kChWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    // (MMA-side barriers take one commit from each issuer thread: CL of them)
+    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], CL); }
     mbar_init(in_full, 1);
-    mbar_init(in_empty, 1);
-    for (int h = 0; h < 2; ++h) { mbar_init(&acc_full[h], 1); mbar_init(&epi_done[h], 8); }
-    mbar_init(slab01_free, 1);
+    mbar_init(in_empty, CL);
+    for (int h = 0; h < 2; ++h) { mbar_init(&acc_full[h], CL); mbar_init(&epi_done[h], 8 * CL); }
+    mbar_init(slab01_free, CL);
     fence_barrier_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 1) {
+    if (CL == 2) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernels' output
   if (MODE == CH_FWD) {
     float* sb = reinterpret_cast<float*>(smem + kChBiasOff);
@@ -119,7 +136,8 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       sb[i] = jobs.c[i >> 10].u[(i >> 8) & 3].bias[i & 255];
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL == 2) cluster_sync_all();        // the peer's barriers must be initialised before anything is signalled on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -128,25 +146,30 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     if (lane == 0) {
       uint32_t wit = 0, n_in = 0;
       auto load_w = [&](const CUtensorMap* tm, int k, int h) {
-        const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+        const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
         mbar_wait(&w_empty[s], ph ^ 1);
-        if ((jobs.dbg & 2) && wit >= kChWStages) { mbar_arrive(&w_full[s]); ++wit; return; }
-        mbar_expect_tx(&w_full[s], kChWStage);
-        tma_load_2d_hint(smem + kChWOff + s * kChWStage, tm, k * kChunkK, h * 128, &w_full[s], kEvictLast);
+        if (CL == 1 && (jobs.dbg & 2) && wit >= kStages) { mbar_arrive(&w_full[s]); ++wit; return; }
+        if (rank == 0) mbar_expect_tx(&w_full[s], kChWStage);           // (both CTAs' halves land on the leader's barrier)
+        if (CL == 2) tma_load_2d_2sm(smem + kChWOff + s * kStageBytes, tm, k * kChunkK, h * 128 + (int)rank * 64, &w_full[s], kEvictLast);
+        else tma_load_2d_hint(smem + kChWOff + s * kStageBytes, tm, k * kChunkK, h * 128, &w_full[s], kEvictLast);
         ++wit;
       };
       auto load_in = [&](int item) {
         const ChainJob& J = jobs.c[item / n_pairs];
-        const int tile0 = 2 * (item % n_pairs);
-        const bool two = tile0 + 1 < jobs.n_tiles;
+        const int g0 = kGroup * (item % n_pairs);                       // first tile of the work item
+        const int tile0 = g0 + 2 * (int)rank;                           // this CTA's two tiles
+        const int n_valid = min(kGroup, jobs.n_tiles - g0);
         mbar_wait(in_empty, (n_in & 1) ^ 1);
-        mbar_expect_tx(in_full, two ? 2 * kChSlab : kChSlab);
-        tma_load_2d_hint(smem + kChInOff, &J.tmIn, 0, tile0 * kTileM, in_full, kEvictFirst);
-        if (two) tma_load_2d_hint(smem + kChInOff + kChSlab, &J.tmIn, 0, (tile0 + 1) * kTileM, in_full, kEvictFirst);
+        if (rank == 0) mbar_expect_tx(in_full, (uint32_t)n_valid * kChSlab);
+        for (int t = 0; t < 2; ++t)
+          if (tile0 + t < jobs.n_tiles) {
+            if (CL == 2) tma_load_2d_2sm(smem + kChInOff + t * kChSlab, &J.tmIn, 0, (tile0 + t) * kTileM, in_full, kEvictFirst);
+            else tma_load_2d_hint(smem + kChInOff + t * kChSlab, &J.tmIn, 0, (tile0 + t) * kTileM, in_full, kEvictFirst);
+          }
         ++n_in;
       };
-      if ((int)blockIdx.x < n_items) load_in(blockIdx.x);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      if (cid < n_items) load_in(cid);
+      for (int item = cid; item < n_items; item += ncl) {
         const ChainJob& J = jobs.c[item / n_pairs];
         load_w(&J.u[0].tmW, 0, 0);
         load_w(&J.u[0].tmW, 0, 1);
@@ -154,75 +177,94 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           for (int h = 0; h < 2; ++h)
             for (int k = 0; k < 4; ++k) load_w(&J.u[u].tmW, k, h);
           // the next pair's input as soon as unit 0 of this pair has consumed the buffer (in_empty): long before it is needed
-          if (u == 1 && item + (int)gridDim.x < n_items) load_in(item + gridDim.x);
+          if (u == 1 && item + ncl < n_items) load_in(item + ncl);
         }
         if (kOut) {
-          const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+          const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
           mbar_wait(&w_empty[s], ph ^ 1);
-          if (jobs.dbg & 2) { mbar_arrive(&w_full[s]); ++wit; continue; }
-          mbar_expect_tx(&w_full[s], 4 * 2048);
-          for (int k = 0; k < 4; ++k)
-            tma_load_2d_hint(smem + kChWOff + s * kChWStage + k * 2048, &J.tmWout, k * kChunkK, 0, &w_full[s], kEvictLast);
+          if (CL == 1 && (jobs.dbg & 2)) { mbar_arrive(&w_full[s]); ++wit; continue; }
+          if (rank == 0) mbar_expect_tx(&w_full[s], 4 * 2048);
+          for (int k = 0; k < 4; ++k) {          // (CL = 2: this CTA's 8 of the 16 hi/lo rows, 1 KB per K chunk)
+            if (CL == 2) tma_load_2d_2sm(smem + kChWOff + s * kStageBytes + k * 1024, &J.tmWout, k * kChunkK, (int)rank * 8, &w_full[s], kEvictLast);
+            else tma_load_2d_hint(smem + kChWOff + s * kStageBytes + k * 2048, &J.tmWout, k * kChunkK, 0, &w_full[s], kEvictLast);
+          }
           ++wit;
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = idesc_bf16(kTileM, 128, 0, 0);
-      constexpr uint32_t idesc_out = idesc_bf16(kTileM, 16, 0, 0);
+  } else if (warp == 1 || (CL == 2 && warp == 10)) {
+    // ------------------------------------------------------------------ MMA issuer(s).  CL = 1: warp 1 issues for both tiles.
+    // CL = 2: in the leader CTA only, warp 1 issues the MMAs of tile 0 (of both CTAs), warp 10 those of tile 1: one thread
+    // cannot issue the 64 MMAs of a unit faster than ~90 cycles each; the two tiles' accumulators are independent, so the
+    // two streams need no mutual order, and every MMA-side barrier takes one commit from each issuer.
+    if (lane == 0 && rank == 0) {
+      const uint32_t mi = warp == 1 ? 0u : 1u;
+      constexpr uint32_t idesc = idesc_bf16(kTileM * CL, 128, 0, 0);
+      constexpr uint32_t idesc_out = idesc_bf16(kTileM * CL, 16, 0, 0);
+      auto mma = [&](uint32_t d, uint64_t da, uint64_t db, uint32_t id, uint32_t acc) {
+        if (CL == 2) umma_bf16_2sm(d, da, db, id, acc); else umma_bf16(d, da, db, id, acc);
+      };
+      auto commit = [&](uint64_t* bar) { if (CL == 2) umma_commit_2sm(bar); else umma_commit(bar); };
+      auto wait_x = [&](uint64_t* bar, uint32_t parity) {      // barriers the peer CTA signals too (plain acquire, as CUTLASS)
+        if (CL == 2 && (jobs.dbg & 8)) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+      };
       uint32_t wit = 0, n_in = 0, c_epi0 = 0, c_epi1 = 0;
       long long w_wait = 0;
       auto wait_epi = [&](int h) {
-        mbar_wait(&epi_done[h], (h ? c_epi1 : c_epi0) & 1);
+        wait_x(&epi_done[h], (h ? c_epi1 : c_epi0) & 1);
         if (h) ++c_epi1; else ++c_epi0;
         tc_fence_after();
       };
       // one weight chunk against the same K slab of both tiles
       auto mma_chunk = [&](uint32_t a0, uint32_t a1, int h, bool first) {
-        const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
+        const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
         const long long tw0 = jobs.trace ? clock64() : 0;
-        mbar_wait(&w_full[s], ph);
+        wait_x(&w_full[s], ph);
         if (jobs.trace) w_wait += clock64() - tw0;
         tc_fence_after();
-        const uint64_t db = smem_desc_sw128(s_w + s * kChWStage, 16, 1024);
-        const uint64_t d0 = smem_desc_sw128(a0, 16, 1024);
-        const uint64_t d1 = smem_desc_sw128(a1, 16, 1024);
+        const uint64_t db = smem_desc_sw128(s_w + s * kStageBytes, 16, 1024);
+        // Every MMA unconditionally, also for tile 1 of a work item whose second tile does not exist (its accumulators are
+        // then never read): a branch around tcgen05.mma is if-converted by ptxas 12.9 into predicated UTCHMMAs whose
+        // descriptor R2URs hang on an unrelated predicate (observed: stale A/B descriptors, wrong results).
+        if (CL == 1) {
+          const uint64_t d0 = smem_desc_sw128(a0, 16, 1024);
+          const uint64_t d1 = smem_desc_sw128(a1, 16, 1024);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + h * 128, d0 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
-        // Tile 1 unconditionally, also when the pair has only one tile (its accumulators are then never read): a branch
-        // here is if-converted by ptxas 12.9 into predicated UTCHMMAs whose descriptor R2URs hang on an unrelated predicate
-        // (observed: stale A/B descriptors, wrong results) — keep every tcgen05.mma of this kernel unconditional.
+          for (int j = 0; j < 4; ++j) mma(tmem_base + h * 128, d0 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + 256 + h * 128, d1 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
-        umma_commit(&w_empty[s]);
+          for (int j = 0; j < 4; ++j) mma(tmem_base + 256 + h * 128, d1 + 2 * j, db + 2 * j, idesc, !(first && j == 0));
+        } else {
+          const uint64_t da = smem_desc_sw128(a0 + mi * (a1 - a0), 16, 1024);      // this issuer's tile (arithmetic, no branch)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma(tmem_base + mi * 256 + h * 128, da + 2 * j, db + 2 * j, idesc, !(first && j == 0));
+        }
+        commit(&w_empty[s]);
         ++wit;
       };
       bool first_item = true;
       int it_no = 0;
       auto stamp = [&](int u, int h, int e) {
-        if (jobs.trace && blockIdx.x == 0 && it_no < 2) {
+        if (jobs.trace && blockIdx.x == 0 && it_no < 2 && mi == 0) {
           jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + e] = clock64();
           if (e == 1) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 3] = jobs.trace[0] + w_wait;   // cumulative wait on weight chunks
         }
       };
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, first_item = false, ++it_no) {
+      for (int item = cid; item < n_items; item += ncl, first_item = false, ++it_no) {
         // ---- unit 0: K = 64 from the input buffer
-        mbar_wait(in_full, n_in & 1);
+        wait_x(in_full, n_in & 1);
         ++n_in;
         tc_fence_after();
         if (!first_item && !kOut) wait_epi(0);          // acc[.][0] drained (last unit of the previous pair)
         stamp(0, 0, 0);
         mma_chunk(s_in, s_in + kChSlab, 0, true);
-        umma_commit(&acc_full[0]);
+        commit(&acc_full[0]);
         stamp(0, 0, 1);
         if (!first_item) wait_epi(1);                   // acc[.][1] drained (output unit / last unit of the previous pair)
         stamp(0, 1, 0);
         mma_chunk(s_in, s_in + kChSlab, 1, true);
-        umma_commit(&acc_full[1]);
+        commit(&acc_full[1]);
         stamp(0, 1, 1);
-        umma_commit(in_empty);
+        commit(in_empty);
         // ---- units 1..3: K = 256 from the activation slabs the previous unit's epilogue wrote in place
         for (int u = 1; u < kChUnits; ++u) {
           wait_epi(0);                                  // slabs 0,1 written, acc[.][0] drained
@@ -233,40 +275,42 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           stamp(u, 0, 2);
           mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, 0, false);
           mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, 0, false);
-          umma_commit(&acc_full[0]);
+          commit(&acc_full[0]);
           stamp(u, 0, 1);
           stamp(u, 1, 0);
           mma_chunk(s_act + 0 * kChSlab, s_act + 4 * kChSlab, 1, true);
           mma_chunk(s_act + 1 * kChSlab, s_act + 5 * kChSlab, 1, false);
-          umma_commit(slab01_free);                     // the half-0 epilogue may now overwrite slabs 0,1
+          commit(slab01_free);                     // the half-0 epilogue may now overwrite slabs 0,1
           mma_chunk(s_act + 2 * kChSlab, s_act + 6 * kChSlab, 1, false);
           mma_chunk(s_act + 3 * kChSlab, s_act + 7 * kChSlab, 1, false);
-          umma_commit(&acc_full[1]);
+          commit(&acc_full[1]);
           stamp(u, 1, 1);
         }
         if (kOut) {
           // ---- output layer: N = 16 (rows 0..7 hi, 8..15 lo halves of the <= 4 real output rows), accumulators in acc[.][1]
           wait_epi(0);
           wait_epi(1);
-          const uint32_t s = wit % kChWStages, ph = (wit / kChWStages) & 1;
-          mbar_wait(&w_full[s], ph);
+          const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
+          wait_x(&w_full[s], ph);
           tc_fence_after();
 #pragma unroll
-          for (int t = 0; t < 2; ++t)
+          for (int tt = 0; tt < (CL == 1 ? 2 : 1); ++tt) {
+            const uint32_t t = CL == 1 ? (uint32_t)tt : mi;          // CL = 2: this issuer's tile
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const uint64_t da = smem_desc_sw128(s_act + (t * 4 + k) * kChSlab, 16, 1024);
-              const uint64_t db = smem_desc_sw128(s_w + s * kChWStage + k * 2048, 16, 1024);
+              const uint64_t db = smem_desc_sw128(s_w + s * kStageBytes + k * (2048 / CL), 16, 1024);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) umma_bf16(tmem_base + t * 256 + 128, da + 2 * j, db + 2 * j, idesc_out, (k | j) != 0);
+              for (int j = 0; j < 4; ++j) mma(tmem_base + t * 256 + 128, da + 2 * j, db + 2 * j, idesc_out, (k | j) != 0);
             }
-          umma_commit(&w_empty[s]);
+          }
+          commit(&w_empty[s]);
           ++wit;
-          umma_commit(&acc_full[1]);
+          commit(&acc_full[1]);
         }
       }
     }
-  } else {
+  } else if (warp < 10) {
     // ------------------------------------------------------------------ epilogue: group = tile of the pair, thread = row
     const int q = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -276,13 +320,14 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
     uint32_t c_acc0 = 0, c_acc1 = 0, c_free = 0;
     int it_no = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it_no) {
+    const uint32_t epi_bar0 = CL == 2 ? mapa_u32(smem_u32(&epi_done[0]), 0) : 0u;     // the leader CTA's epi_done[0]
+    for (int item = cid; item < n_items; item += ncl, ++it_no) {
       const bool tr = jobs.trace && blockIdx.x == 0 && it_no < 2 && (threadIdx.x == 64 || threadIdx.x == 192);
       auto stamp = [&](int u, int h, int e) {
         if (tr) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 4 + grp * 6 + e] = clock64();
       };
       const ChainJob& J = jobs.c[item / n_pairs];
-      const int tile = 2 * (item % n_pairs) + grp;
+      const int tile = kGroup * (item % n_pairs) + 2 * (int)rank + grp;
       const bool valid = tile < jobs.n_tiles;
       const size_t grow = (size_t)tile * kTileM + r;
       for (int u = 0; u < kChUnits; ++u) {
@@ -358,7 +403,9 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           stamp(u, h, 4);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&epi_done[h]);        // the MMA warp may read the slabs / overwrite the accumulators
+          if (lane == 0) {                                 // the MMA warp may read the slabs / overwrite the accumulators
+            if (CL == 2) mbar_arrive_cluster(epi_bar0 + 8 * h); else mbar_arrive(&epi_done[h]);
+          }
           if (valid) {
             named_bar_sync(3 + grp, 128);                  // all 128 rows of both slabs are in SMEM
             if (gleader && !(jobs.dbg & 1)) {
@@ -386,14 +433,20 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&epi_done[1]);
+        if (lane == 0) {
+          if (CL == 2) mbar_arrive_cluster(epi_bar0 + 8); else mbar_arrive(&epi_done[1]);
+        }
       }
     }
     if (gleader) bulk_wait<0>();
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (CL == 2) cluster_sync_all();        // the peer may still signal this CTA's barriers / read its SMEM until here
+  else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (CL == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+  }
 }
 
 }  // namespace tc

@@ -73,14 +73,16 @@ def test_step_bf16_chunked(name):
     eng.close()
 
 
+@pytest.mark.parametrize("cl", ["2", "1"])
 @pytest.mark.parametrize("name", ["mid_mask_c2f", "implicit_edges"])
-def test_fused_chain_matches_per_layer_kernels(name, monkeypatch):
-    """The layer-fused chain kernel (k_tc_chain: activations resident in SMEM) against the per-layer GEMM launches
+def test_fused_chain_matches_per_layer_kernels(name, cl, monkeypatch):
+    """The layer-fused chain kernel (k_tc_chain: activations resident in SMEM; both its CTA-pair and its single-CTA variant) against the per-layer GEMM launches
     (MARF_NO_FUSE=1): the hidden layers run the same bf16 MMAs in the same K order, only the 3-/1-wide output layer
     differs (hi/lo bf16 weight rows on the tensor core instead of fp32 FMAs), so the results agree far below the
     bf16-vs-oracle tolerance."""
     import gpu_util
     cfg, params, images, it, progress, g = cases.build_case(name)
+    monkeypatch.setenv("MARF_CHAIN_CL", cl)       # 2: CTA pairs with cta_group::2 MMAs (the default), 1: one CTA per tile pair
     eng = gpu_util.make_engine(cfg, "bf16")
     fused = gpu_util.run_step(eng, cfg, params, images, it, progress)
     eng.close()
