@@ -20,11 +20,12 @@ def run(mode, iters, args):
     from marf_b200.attrdict import AttrDict
     opt = options.load_options("options/planar.yaml")
     opt.update(model="planar", yaml="planar", H=args.H, W=args.W, patch_H=args.H // 2, patch_W=args.W // 2, batch_size=5,
-               use_masks=args.occluders, use_implicit_mask=False, use_edges=False, barf_c2f=[0.0, 0.4], max_iter=iters,
+               use_masks=args.occluders or args.implicit, use_implicit_mask=args.implicit, use_edges=args.implicit,
+               barf_c2f=[0.0, 0.4], max_iter=iters,
                use_homographies=False, precision=mode, device="cuda:0", output_path=f"/tmp/marf_conv_{mode}", tb=None, seed=3,
                world_size=1, rank=0, fused_optimizer=True)
     opt.warp.noise_h, opt.warp.noise_t = args.noise_h, args.noise_t
-    opt.synthetic = dict(enabled=True, seed=args.scene_seed, occluders=args.occluders)
+    opt.synthetic = dict(enabled=True, seed=args.scene_seed, occluders=args.occluders or args.implicit)
     opt.freq.scalar = 10 ** 9
     opt.freq.vis = 10 ** 9
     os.makedirs(opt.output_path, exist_ok=True)
@@ -37,9 +38,12 @@ def run(mode, iters, args):
     m.timer = AttrDict(start=time.time(), it_mean=None)
     var = AttrDict(idx=torch.arange(opt.batch_size), images=m.images)
     hist = []
+    tail = []                                  # rgb loss of the last 200 iterations (PSNR of their mean: a steadier end point)
     t0 = time.time()
     for it in range(iters):
         loss = m.train_iteration(var, None)
+        if it >= iters - 200:
+            tail.append(loss.rgb.detach())
         if opt.warp.fix_first:
             m.graph.warp_param.weight.data[0] = 0
         if (it + 1) % args.every == 0 or it == 0:
@@ -48,7 +52,9 @@ def run(mode, iters, args):
             hist.append(dict(it=it + 1, corner_px=err, psnr=psnr, loss=float(loss.all)))
             print(f"[{mode}] it {it+1:5d}  corner error {err:7.3f} px   PSNR {psnr:6.2f} dB   loss {float(loss.all):.5f}", flush=True)
     torch.cuda.synchronize()
-    return dict(mode=mode, seconds=time.time() - t0, hist=hist)
+    psnr_tail = float(-10 * torch.stack(tail).double().mean().log10()) if tail else float("nan")
+    print(f"[{mode}] PSNR of the mean rgb loss over the last {len(tail)} iterations: {psnr_tail:.2f} dB", flush=True)
+    return dict(mode=mode, seconds=time.time() - t0, hist=hist, psnr_last200=psnr_tail)
 
 
 if __name__ == "__main__":
@@ -62,6 +68,7 @@ if __name__ == "__main__":
     ap.add_argument("--noise_t", type=float, default=0.2)
     ap.add_argument("--scene_seed", type=int, default=0)
     ap.add_argument("--occluders", action="store_true")
+    ap.add_argument("--implicit", action="store_true", help="learned occlusion mask (mask head + edge term), occluders pasted in")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
     res = [run(mode, a.iters, a) for mode in a.modes.split(",")]
