@@ -113,10 +113,10 @@ def roofline_lines(wl, kern, pk, rows_per_gpu, step_tflops, args):
     `step_roofline` keeps the whole-step figure (algorithmic FLOP of the step / step time vs the tensor peak).
     Algorithmic bytes / FLOP per pixel-sample row (h = hidden layers, all 256 wide, two chains when
     the mask head is on):
-      k_tc_dw          : reads X_l and dY_l of every 256x256 layer (1024 B), of the output layers (X 512 B + dlogits tile 128 B)
+      k_tc_dw          : reads X_l and dY_l of every 256x256 layer (1024 B), of the output layers (X 512 B + dlogits tile 16 B)
                          and of layer 0 (dY_0 512 B + 64-wide input 128 B)
       k_tc_chain<fwd>  : reads the 64-wide input (128 B), writes 4 activations (2048 B) + 4 mask-bit rows (128 B) + logits (16 B)
-      k_tc_chain<dx>   : reads the dlogits tile (128 B) + 4 mask-bit rows (128 B), writes 4 dY (2048 B)
+      k_tc_chain<dx>   : reads the dlogits tile (16 B) + 4 mask-bit rows (128 B), writes 4 dY (2048 B)
       k_tc_gemm<64,wg> : reads dY_0 (512 B)
     traffic (DRAM bytes per launch from ncu) is read from profiles/r01_kernel_traffic.json when it holds this workload."""
     out = {}
@@ -131,9 +131,9 @@ def roofline_lines(wl, kern, pk, rows_per_gpu, step_tflops, args):
     width = wl["layers"][0]
     hidden = len(wl["layers"]) - 1
     rows = (rows_per_gpu + 127) // 128 * 128
-    byt = {"k_tc_dw": chains * ((hidden - 1) * 4 * width + 2 * (2 * width + 128)),
+    byt = {"k_tc_dw": chains * ((hidden - 1) * 4 * width + (2 * width + 16) + (2 * width + 128)),
            "k_tc_chain<fwd>": chains * (128 + hidden * 2 * width + hidden * width // 8 + 16),
-           "k_tc_chain<dx>": chains * (128 + hidden * width // 8 + hidden * 2 * width),
+           "k_tc_chain<dx>": chains * (16 + hidden * width // 8 + hidden * 2 * width),
            "k_tc_gemm<64,warp_grad>": 2 * width}
     flop = {"k_tc_dw": chains * 2 * ((hidden - 1) * width * width + width * (3 if chains == 1 else 2) + width * 64),
             "k_tc_chain<fwd>": chains * 2 * (64 * width + (hidden - 1) * width * width + width * (3 if chains == 1 else 2)),

@@ -444,7 +444,7 @@ struct BfChain {
   uint32_t* flags_bwd[MARF_MAX_LAYERS] = {};       // flags_bwd[l]: per-tile completion counters of dY[l] (written by dX of layer l+1)
   float* logits = nullptr;                // [chunk,4] fp32
   float* dlogits = nullptr;               // [chunk,4] fp32
-  bf16* dl16 = nullptr;                   // [chunk,64] bf16 copy of dlogits (zero padded): A operand of the output layer's dW / dX
+  bf16* dl16 = nullptr;                   // [chunk,8] bf16 copy of dlogits: A operand of the output layer's dW / dX (64-wide TMA boxes, OOB zero fill)
   CUtensorMap tmDL64, tmDL128;
   bf16* Wlast_t = nullptr;                // [k_in(last), 64] bf16: W_last^T zero padded (B operand of the output layer's dX GEMM)
   CUtensorMap tmWlast_t, tmWlast128, tmWlast64;
@@ -559,11 +559,12 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
   }
   B.logits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
   B.dlogits = (float*)ws_alloc(h, (size_t)h->chunk * 4 * sizeof(float));
-  B.dl16 = (bf16*)ws_alloc(h, (size_t)h->chunk * 64 * 2);
+  // dlogits as an MMA operand: 8 bf16 per row in HBM; the 64-column TMA boxes zero-fill the other 56 (out of bounds)
+  B.dl16 = (bf16*)ws_alloc(h, (size_t)h->chunk * 8 * 2);
   if (!B.logits || !B.dlogits || !B.dl16) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (logits)");
-  int rc = make_tmap(h, S, &B.tmDL64, B.dl16, h->chunk, 64, 64);
+  int rc = make_tmap(h, S, &B.tmDL64, B.dl16, h->chunk, 8, 64);
   if (rc) return rc;
-  rc = make_tmap(h, S, &B.tmDL128, B.dl16, h->chunk, 64, 128);
+  rc = make_tmap(h, S, &B.tmDL128, B.dl16, h->chunk, 8, 128);
   if (rc) return rc;
   const int kl = B.L[F.n - 1].k_in;
   if (kl == 256) {

@@ -620,7 +620,8 @@ struct GradArgs {
   int label_channels;
   float* dlogits; int dld;     // out [n_pad, dld]
   float* dmlogits; int dmld;   // out [n_pad, dmld] (implicit only)
-  __nv_bfloat16* dl_bf16;      // optional bf16 copies [n_pad, 64] (zero padded) for the tensor-core dW of the output layers
+  __nv_bfloat16* dl_bf16;      // optional bf16 copies [n_pad, 8] for the tensor-core dX / dW of the output layers (the TMA
+                               // boxes over them are 64 columns wide: columns >= 8 are out-of-bounds zero fill, not HBM reads)
   __nv_bfloat16* dml_bf16;
 };
 
@@ -630,9 +631,8 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
   if (t >= rg.padded) return;
   float* dl = a.dlogits + (size_t)t * a.dld;
   float* dm = a.dmlogits ? a.dmlogits + (size_t)t * a.dmld : nullptr;
-  uint4* dlb = a.dl_bf16 ? reinterpret_cast<uint4*>(a.dl_bf16 + (size_t)t * 64) : nullptr;
-  uint4* dmb = a.dml_bf16 ? reinterpret_cast<uint4*>(a.dml_bf16 + (size_t)t * 64) : nullptr;
-  // (columns 8..63 of the bf16 copies are zero from allocation and never written)
+  uint4* dlb = a.dl_bf16 ? reinterpret_cast<uint4*>(a.dl_bf16 + (size_t)t * 8) : nullptr;
+  uint4* dmb = a.dml_bf16 ? reinterpret_cast<uint4*>(a.dml_bf16 + (size_t)t * 8) : nullptr;
   if (t >= rg.count) {
     for (int j = 0; j < a.dld; ++j) dl[j] = 0.f;
     if (dm) for (int j = 0; j < a.dmld; ++j) dm[j] = 0.f;
