@@ -295,15 +295,32 @@ def run_marf(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values()) * world     # whole job, bytes per step
     d2h = 8 * world
 
-    # the loss of every step is read back (D2H into pinned memory); the host consumes it one step later so that
-    # Python/launch overhead overlaps the GPU's work on the next step
+    # Input prefetch, as a training data loader does it: the targets of step i+1 are copied host->device on a copy stream into
+    # the second of two device buffers while step i computes (every step's H2D copy is inside the timed region; a buffer is
+    # refilled only after the step that read it has finished).  The loss of every step is read back (D2H into pinned
+    # memory); the host consumes it one step later so that Python/launch overhead overlaps the GPU's work on the next step.
+    copy_st = torch.cuda.Stream(device=device)
+    bufs = [loc.rgb, torch.empty_like(loc.rgb)]
+    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+    for ev in ev_free:
+        ev.record(st)
     loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
     loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
     seen = []
 
+    def prefetch(i):
+        with torch.cuda.stream(copy_st):
+            copy_st.wait_event(ev_free[i & 1])
+            bufs[i & 1].copy_(host["rgb"], non_blocking=True)         # H2D of step i's targets (this rank's shard)
+            ev_copied[i & 1].record(copy_st)
+
     def e2e_step(i):
-        loc.rgb.copy_(host["rgb"], non_blocking=True)               # H2D of the step's targets (this rank's shard)
+        st.wait_event(ev_copied[i & 1])
+        loc.rgb = bufs[i & 1]
+        prefetch(i + 1)
         loss = m.train_iteration(var, None)
+        ev_free[i & 1].record(st)
         if opt.warp.fix_first and m.fused_tail is None:
             g.warp_param.weight.data[0] = 0
         loss_host[i & 1].copy_(loss.all.detach().reshape(1), non_blocking=True)   # D2H of the step's result
@@ -312,6 +329,7 @@ def run_marf(args):
             loss_ev[(i - 1) & 1].synchronize()
             seen.append(float(loss_host[(i - 1) & 1]))
 
+    prefetch(0)
     for i in range(3):
         e2e_step(i)
     barrier()
@@ -359,8 +377,9 @@ def run_marf(args):
                                 wall_s_timed_loop=wall),
                     clocks=clocks,
                     e2e=dict(value=e2e_value, unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms, what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first), targets copied "
-                                  "from pinned host memory and the loss read back every step (consumed one step later)"),
+                             ms_per_step=e2e_ms, what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first); every step's targets are copied "
+                                  "from pinned host memory (prefetched on a copy stream during the previous step, double-buffered) and the "
+                                  "loss is read back every step (consumed one step later)"),
                     gpu_launches=launches)
         line.update(roofline_lines(wl, kern, pk, n_px_total // world, tflops, args))
         if args.gpus == 1 and not args.no_cpu:

@@ -190,6 +190,12 @@ typedef struct marf_adam_io {
 } marf_adam_io;
 int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream);
 
+/* Loss scalars of the last step from its device-side sums, one launch (replaces the dozen 0-dim tensor ops of
+ * Graph.compute_loss model/planar.py:362-378 + Model.summarize_loss :172-185): out5 = {rgb, mask, edge, render, all} with
+ * render = (1-alpha) rgb + 0.5 mask + alpha edge and all = w[0] render + w[1] rgb + w[2] mask + w[3] edge
+ * (w = 10**loss_weight, 0 for a disabled term; host array).  sums/out5 are device pointers. */
+int marf_loss_scalars(marf_handle* h, const double* sums, double alpha, const double* weights4, double* out5, void* stream);
+
 /* diagnostic: run ONE tensor-core kernel (tcgen05) on fp32 device arrays that are rounded to bf16 inside.
  * mode 0: relu(A[rows,K] W[N,K]^T + aux[N]); 1: (A W^T)*(aux[rows,N]>0); 2: plain fp32 out, N=64;
  * 3: out[N,K] = A[rows,N]^T aux[rows,K] (the dW kernel).  Synchronises `stream`.  Used by tests/ only. */

@@ -682,6 +682,28 @@ __global__ void k_adam(const __grid_constant__ AdamTable t) {
   }
 }
 
+// loss scalars from the sums the step left on the device (model/planar.py:362-378 and :172-185) in one launch:
+// out = {rgb, mask, edge, render = (1-alpha) rgb + 0.5 mask + alpha edge, all = sum_k weight_k loss_k}
+static __global__ void k_loss_scalars(const double* __restrict__ sums, int implicit, int use_edges, double alpha, double w_render,
+                                      double w_rgb, double w_mask, double w_edge, double* __restrict__ out) {
+  pdl_wait();
+  const double rgb = sums[MARF_S_RGB] / sums[MARF_N_RGB];
+  const double mask = implicit ? sums[MARF_S_MASK] / sums[MARF_N_MASK] : 0.0;
+  const double edge = use_edges ? sums[MARF_S_EDGE] / sums[MARF_N_EDGE] : 0.0;
+  const double render = (1.0 - alpha) * rgb + 0.5 * mask + alpha * edge;
+  out[0] = rgb; out[1] = mask; out[2] = edge; out[3] = render;
+  out[4] = w_render * render + w_rgb * rgb + w_mask * mask + w_edge * edge;
+}
+
+extern "C" int marf_loss_scalars(marf_handle* h, const double* sums, double alpha, const double* weights4, double* out5, void* stream) {
+  if (!h || !sums || !weights4 || !out5) return MARF_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_k(k_loss_scalars, 1, 1, 0, st, sums, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? 1 : 0, h->cfg.use_edges ? 1 : 0, alpha,
+           weights4[0], weights4[1], weights4[2], weights4[3], out5);
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
+
 extern "C" int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream) {
   if (!h) return MARF_ERR_INVALID;
   if (!io || io->n_tensors <= 0 || io->n_tensors > kMaxAdam || !io->params || !io->grads || !io->exp_avg || !io->exp_avg_sq ||

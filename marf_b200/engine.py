@@ -254,6 +254,14 @@ class PlanarEngine:
         return out
 
     # ------------------------------------------------------------------ loss values from the sums (device, no sync)
+    def loss_scalars(self, sums: torch.Tensor, alpha: float, weights4: Sequence[float], out: torch.Tensor):
+        """out[5] (float64, device) <- {rgb, mask, edge, render, all} from the step's sums in ONE launch (marf_loss_scalars)."""
+        w = (C.c_double * 4)(*[float(x) for x in weights4])
+        L.check(self.lib, self.handle,
+                self.lib.marf_loss_scalars(self.handle, C.c_void_p(sums.data_ptr()), float(alpha), w, C.c_void_p(out.data_ptr()),
+                                           self._stream()), "marf_loss_scalars")
+        return out
+
     def loss_values(self, sums: Optional[torch.Tensor] = None):
         """(rgb, mask, edge) as 0-dim float64 device tensors (model/planar.py:362-370)."""
         s = self.sums if sums is None else sums

@@ -298,6 +298,19 @@ class Graph(torch.nn.Module):
         loss = edict()
         opt = self.opt
         _, _, _, alpha = self.loss_coefficients()
+        if opt.loss_weight.render is not None and not torch.is_grad_enabled():
+            # fused-optimizer path (no autograd graph wanted): all five scalars from one launch; `all` is precomputed for
+            # Model.summarize_loss (which recognises the marker and does not launch a dozen 0-dim tensor ops)
+            lw = opt.loss_weight
+            w4 = [0.0 if lw[k] is None else 10 ** float(lw[k]) for k in ("render", "rgb", "mask", "edge")]
+            self._loss_out = getattr(self, "_loss_out", None)
+            if self._loss_out is None:
+                self._loss_out = torch.zeros(2, 5, dtype=torch.float64, device=self._sums.device)
+            out = self.engine.loss_scalars(self._sums, alpha, w4, self._loss_out[self.it & 1])   # (double-buffered: the caller
+            loss.render, loss.rgb, loss.mask, loss.edge = out[3], out[0], out[1], out[2]          #  may read step i-1's loss late)
+            self._fused_all = out[4]
+            self.it += 1
+            return loss
         if opt.loss_weight.render is not None:
             rgb, mask, edge = self.engine.loss_values(self._sums)
             render = (1 - alpha) * rgb + 0.5 * mask + alpha * edge
@@ -429,8 +442,13 @@ class Model(torch.nn.Module):
     def summarize_loss(self, loss):
         """model/planar.py:172-185 — Σ 10**w · loss[k].  The Inf/NaN asserts of the reference (8 host syncs per
         step) are replaced by the device-side MARF_NONFINITE counter, read with the scalars every freq.scalar steps."""
-        total = 0.
         assert "all" not in loss
+        fused_all = getattr(self.graph, "_fused_all", None)
+        if fused_all is not None and not torch.is_grad_enabled():
+            self.graph._fused_all = None
+            loss.update(all=fused_all)          # computed by marf_loss_scalars with the same weights (Graph.compute_loss)
+            return loss
+        total = 0.
         for key in loss:
             assert key in self.opt.loss_weight
             assert loss[key].shape == ()
