@@ -504,9 +504,11 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
     B.ld[l] = L.kp;
     if (!L.thin) {
       if (l == F.n - 1) return fail(h, MARF_ERR_UNSUPPORTED, "bf16: the last layer must be the 3-/1-wide output layer");
-      if (L.k_out != 256 && L.k_out != 128)
-        return fail(h, MARF_ERR_UNSUPPORTED, "bf16: hidden widths 128 and 256 are implemented (got " + std::to_string(L.k_out) + ")");
-      if (L.kp > 448) return fail(h, MARF_ERR_UNSUPPORTED, "bf16: layer input wider than 448 does not fit the resident-weight tile");
+      if (L.k_out != 256 && L.k_out != 512)
+        return fail(h, MARF_ERR_UNSUPPORTED, "bf16: hidden widths 256 and 512 are implemented (got " + std::to_string(L.k_out) + ")");
+      if (L.kp > 512) return fail(h, MARF_ERR_UNSUPPORTED, "bf16: layer input wider than 512 does not fit the resident-weight tile");
+      if (l >= 1 && L.kp != 256 && L.kp != 512 && !(l == 0))
+        return fail(h, MARF_ERR_UNSUPPORTED, "bf16: hidden layer inputs must be 256 or 512 wide");
       L.Wk = (bf16*)ws_alloc(h, (size_t)L.np * L.kp * 2);
       L.Wt = (bf16*)ws_alloc(h, (size_t)L.kp * L.np * 2);
       if (!L.Wk || !L.Wt) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed");
@@ -742,21 +744,20 @@ static tc::GemmJob fwd_job(BfChain& B, int l, int rows, int n_tile, int n0) {
 // in which layer l+1 consumes layer l's tiles through per-tile flags (L2-resident hand-over).
 static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
   Bf16State* S = h->bf16;
-  for (int ci = 0; ci < n_chains; ++ci) {
-    BfChain& B = *chains[ci];
-    for (int l = 0; l < B.n - 1; ++l) {
-      BfLayer& L = B.L[l];
-      if (!(L.kp > 256 && L.np > 128)) continue;
-      tc::GemmJobs jobs{};
-      int w[tc::kMaxGemmJobs];
-      for (int t = 0; t < L.np / 128; ++t) { jobs.j[jobs.n] = fwd_job(B, l, rows, 128, t * 128); w[jobs.n++] = 1; }
-      assign_ctas(jobs, w, S->num_sms);
-      int smem = tc::gemm_smem(128, L.kp / 64, true).total + 1024;
-      int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
-      launch_k(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
-      BF_LAUNCH(h);
-    }
-  }
+  // a layer whose input is wider than 256 (width-512 networks): N split into 128-column jobs, [128, K] weight tiles resident
+  auto launch_wide = [&](BfChain& B, int l) -> int {
+    BfLayer& L = B.L[l];
+    tc::GemmJobs jobs{};
+    int w[tc::kMaxGemmJobs];
+    if (L.np / 128 > tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: layer too wide");
+    for (int t = 0; t < L.np / 128; ++t) { jobs.j[jobs.n] = fwd_job(B, l, rows, 128, t * 128); w[jobs.n++] = 1; }
+    assign_ctas(jobs, w, S->num_sms);
+    int smem = tc::gemm_smem(128, L.kp / 64, true).total + 1024;
+    int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
+    launch_k(tc::k_tc_gemm<128, tc::EPI_BIAS_RELU>, grid, tc::kThreads, smem, st, jobs);
+    BF_LAUNCH(h);
+    return MARF_OK;
+  };
   // Chained mode (MARF_CHAIN=1, experimental): every remaining layer of every chain in one launch, layer l+1 consuming
   // layer l's tiles through per-tile flags.  Default: one launch per depth level (the same-depth layers of all chains
   // share the SMs); measured faster on B200 because each launch then streams at the full HBM rate.
@@ -776,19 +777,26 @@ static int launch_forward_all(marf_handle* h, cudaStream_t st, BfChain** chains,
       for (int l = 0; l < B.n - 1; ++l) {
         if (!chain_mode && (l != level || ci != only_chain)) continue;
         BfLayer& L = B.L[l];
-        if (L.kp > 256 && L.np > 128) continue;
-        if (L.np != 256) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: hidden width must be 256");
-        if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: too many layers");
-        tc::GemmJob J = fwd_job(B, l, rows, 256, 0);
-        if (chain_mode) {
-          const bool chained_in = l >= 1 && !(B.L[l - 1].kp > 256 && B.L[l - 1].np > 128);
-          J.flags_in = chained_in ? B.flags_fwd[l] : nullptr;
-          J.in_target = 2u;
-          J.flags_out = (l + 1 < B.n - 1) ? B.flags_fwd[l + 1] : nullptr;
+        if (L.kp > 256 && L.np > 128) {
+          if (chain_mode) return fail(h, MARF_ERR_UNSUPPORTED, "MARF_CHAIN does not serve layers wider than 256");
+          int rc = launch_wide(B, l);               // (one layer per pass here: layer order is preserved)
+          if (rc) return rc;
+          continue;
         }
-        w[jobs.n] = 1;                              // the epilogue (same for every layer) bounds a tile, not K
-        max_kc = std::max(max_kc, L.kp / 64);
-        jobs.j[jobs.n++] = J;
+        if (L.np % 256) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: hidden width must be a multiple of 256");
+        for (int t = 0; t < L.np / 256; ++t) {      // (width 512: two 256-column jobs)
+          if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 forward: too many layers");
+          tc::GemmJob J = fwd_job(B, l, rows, 256, t * 256);
+          if (chain_mode && L.np == 256) {
+            const bool chained_in = l >= 1 && !(B.L[l - 1].kp > 256 && B.L[l - 1].np > 128);
+            J.flags_in = chained_in ? B.flags_fwd[l] : nullptr;
+            J.in_target = 2u;
+            J.flags_out = (l + 1 < B.n - 1) ? B.flags_fwd[l + 1] : nullptr;
+          }
+          w[jobs.n] = 1;                            // the epilogue (same for every layer) bounds a tile, not K
+          max_kc = std::max(max_kc, L.kp / 64);
+          jobs.j[jobs.n++] = J;
+        }
       }
     }
     if (jobs.n == 0) continue;
@@ -851,39 +859,47 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     const int only_chain = pass / max_depth, level = max_depth - 1 - pass % max_depth;
     tc::GemmJobs jobs{};
     int w[tc::kMaxGemmJobs];
+    bool wide = false;
+    int max_kc = 4;
     for (int ci = 0; ci < n_chains; ++ci) {
       BfChain& B = *chains[ci];
       for (int l = B.n - 2; l >= 1; --l) {
         if (!chain_mode && (l != level || ci != only_chain)) continue;
         BfLayer& L = B.L[l];
-        if (L.kp != 256 || L.np != 256) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: hidden width must be 256");
-        if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: too many layers");
-        tc::GemmJob J{};
-        J.tmA = B.tmDY128[l];
-        J.tmW = L.tmWt;
-        J.tmOut = B.tmDY128[l - 1];
-        J.p.n_tiles = rows / 128;
-        J.p.k_chunks = L.np / 64;
-        J.p.bits_in = B.bits[l];
-        J.p.bits_ld = B.ld[l] / 32;
-        J.p.reverse = chain_mode ? 0 : (l & 1);      // start where the previous launch just finished (still in L2)
-        J.p.load_policy = tc::kEvictFirst;         // (dY[l] is read again by the dW pass, but long after L2 has turned over)
-        J.p.store_policy = tc::kEvictLast;
-        J.n0 = 0;
-        if (chain_mode) {
-          J.flags_in = l < B.n - 2 ? B.flags_bwd[l] : nullptr;   // dY[n-2] comes from the output-layer kernel (complete)
-          J.in_target = 2u;
-          J.flags_out = l - 1 >= 1 ? B.flags_bwd[l - 1] : nullptr;
+        // 256 -> 256: one job with the whole W^T resident; wider layers: 128-column jobs (W^T tile [128, np] resident)
+        wide = L.kp != 256 || L.np != 256;
+        if (wide && (L.kp % 128 || L.np > 512)) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: layer shape not supported");
+        const int n_tile = wide ? 128 : 256;
+        max_kc = std::max(max_kc, L.np / 64);
+        for (int t = 0; t < L.kp / n_tile; ++t) {
+          if (jobs.n >= tc::kMaxGemmJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dX: too many layers");
+          tc::GemmJob J{};
+          J.tmA = B.tmDY128[l];
+          J.tmW = wide ? L.tmWt128 : L.tmWt;
+          J.tmOut = B.tmDY128[l - 1];
+          J.p.n_tiles = rows / 128;
+          J.p.k_chunks = L.np / 64;
+          J.p.bits_in = B.bits[l];
+          J.p.bits_ld = B.ld[l] / 32;
+          J.p.reverse = chain_mode ? 0 : (l & 1);    // start where the previous launch just finished (still in L2)
+          J.p.load_policy = tc::kEvictFirst;       // (dY[l] is read again by the dW pass, but long after L2 has turned over)
+          J.p.store_policy = tc::kEvictLast;
+          J.n0 = t * n_tile;
+          if (chain_mode && !wide) {
+            J.flags_in = l < B.n - 2 ? B.flags_bwd[l] : nullptr;   // dY[n-2] comes from the output-layer kernel (complete)
+            J.in_target = 2u;
+            J.flags_out = l - 1 >= 1 ? B.flags_bwd[l - 1] : nullptr;
+          }
+          w[jobs.n] = 1;
+          jobs.j[jobs.n++] = J;
         }
-        w[jobs.n] = 1;
-        jobs.j[jobs.n++] = J;
       }
     }
     if (jobs.n == 0) continue;
     assign_ctas(jobs, w, S->num_sms);
-    int smem = tc::gemm_smem(256, 4, true).total + 1024;
     int grid = jobs.j[jobs.n - 1].cta_begin + jobs.j[jobs.n - 1].cta_count;
-    launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, grid, tc::kThreads, smem, st, jobs);
+    if (wide) launch_k(tc::k_tc_gemm<128, tc::EPI_RELU_MASK>, grid, tc::kThreads, tc::gemm_smem(128, max_kc, true).total + 1024, st, jobs);
+    else launch_k(tc::k_tc_gemm<256, tc::EPI_RELU_MASK>, grid, tc::kThreads, tc::gemm_smem(256, 4, true).total + 1024, st, jobs);
     BF_LAUNCH(h);
   }
   return launch_dx0(h, st, chains, n_chains, rows, rg);
@@ -894,17 +910,16 @@ static int launch_dx_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
 static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, long long row_first) {
   Bf16State* S = h->bf16;
   (void)row_first;
-  tc::DwJobs jobs{};
-  int nj = 0;
-  int weight[tc::kDwMaxJobs];
-  auto add = [&](const CUtensorMap& tmDY, const CUtensorMap& tmX, int n_tile, int m_valid, int n_valid, int n0, int ld_w, int do_bias,
-                 float* dW, float* db) -> bool {
-    if (nj >= tc::kDwMaxJobs) return false;
-    tc::DwJob& J = jobs.j[nj];
-    J.tmDY = tmDY; J.tmX = tmX; J.rows = rows; J.n_tile = n_tile; J.m_halves = (m_valid + 127) / 128; J.m_valid = m_valid;
+  std::vector<tc::DwJob> all;
+  std::vector<int> weight;
+  auto add = [&](const CUtensorMap& tmDY, const CUtensorMap& tmX, int n_tile, int m0, int m_layer, int n_valid, int n0, int ld_w,
+                 int do_bias, float* dW, float* db) {
+    tc::DwJob J{};
+    J.tmDY = tmDY; J.tmX = tmX; J.rows = rows; J.n_tile = n_tile; J.m0 = m0;
+    J.m_halves = (std::min(m_layer - m0, 256) + 127) / 128; J.m_valid = m_layer;
     J.n_valid = n_valid; J.n0 = n0; J.ld_w = ld_w; J.do_bias = do_bias; J.dW = dW; J.db = db;
-    weight[nj++] = J.m_halves * 128 + n_tile;            // bytes per pixel row ~ (dY columns + X columns)
-    return true;
+    all.push_back(J);
+    weight.push_back(J.m_halves * 128 + n_tile);         // bytes per pixel row ~ (dY columns + X columns)
   };
   for (int ci = 0; ci < n_chains; ++ci) {
     BfChain& B = *chains[ci];
@@ -912,55 +927,58 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
     if (B.L[B.n - 1].k_in == 256) {
       // output layer (3-/1-wide): dW = dlogits^T X_last through the same kernel (dlogits as a zero-padded bf16 tile)
       const int l = B.n - 1;
-      if (!add(B.tmDL64, B.tmAct64[l], 256, B.L[l].k_out, B.L[l].k_in, 0, F.ld_in[l], 1, F.gWp[l], F.gbp[l]))
-        return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
+      add(B.tmDL64, B.tmAct64[l], 256, 0, B.L[l].k_out, B.L[l].k_in, 0, F.ld_in[l], 1, F.gWp[l], F.gbp[l]);
     }
     for (int l = 0; l < B.n - 1; ++l) {
       BfLayer& L = B.L[l];
       const int n_tile = L.kp >= 256 ? 256 : 64;
       if (n_tile == 64 && L.kp != 64) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: input width must be 64 or >= 256");
       const int n_tiles_n = (L.kp + n_tile - 1) / n_tile;
-      for (int t = 0; t < n_tiles_n; ++t) {
-        bool ok;
-        if (l == 0 && B.col_off0 > 0)
-          // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
-          // k_mask_dw_finalize turns into dW0 / db0
-          ok = add(B.tmDY64[l], B.tmAct64[l], n_tile, L.k_out, 64, t * n_tile, 64, 0, B.dW0x, F.gbp[l]);
-        else
-          ok = add(B.tmDY64[l], B.tmAct64[l], n_tile, L.k_out, L.k_in, t * n_tile, F.ld_in[l], t == 0, F.gWp[l], F.gbp[l]);
-        if (!ok) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 dW: too many layers for one launch");
-      }
+      for (int m0 = 0; m0 < L.k_out; m0 += 256)          // (outputs wider than 256: one job per 256 output features)
+        for (int t = 0; t < n_tiles_n; ++t) {
+          if (l == 0 && B.col_off0 > 0)
+            // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
+            // k_mask_dw_finalize turns into dW0 / db0
+            add(B.tmDY64[l], B.tmAct64[l], n_tile, m0, L.k_out, 64, t * n_tile, 64, 0, B.dW0x, F.gbp[l]);
+          else
+            add(B.tmDY64[l], B.tmAct64[l], n_tile, m0, L.k_out, L.k_in, t * n_tile, F.ld_in[l], t == 0, F.gWp[l], F.gbp[l]);
+        }
     }
   }
-  if (nj == 0) return MARF_OK;
-  jobs.n = nj;
-  // CTAs per job proportional to the bytes it streams (largest-remainder rounding so that every SM gets a CTA)
-  int wsum = 0;
-  for (int i = 0; i < nj; ++i) wsum += weight[i];
-  int cnt[tc::kDwMaxJobs], rem[tc::kDwMaxJobs], used = 0;
-  for (int i = 0; i < nj; ++i) {
-    const long long x = (long long)S->num_sms * weight[i];
-    cnt[i] = std::max(1, (int)(x / wsum));
-    rem[i] = (int)(x % wsum);
-    used += cnt[i];
+  // ONE launch when the jobs fit the kernel's parameter table (the 256-wide networks: 10 jobs), else several
+  for (size_t first = 0; first < all.size(); first += tc::kDwMaxJobs) {
+    const int nj = (int)std::min<size_t>(tc::kDwMaxJobs, all.size() - first);
+    tc::DwJobs jobs{};
+    jobs.n = nj;
+    for (int i = 0; i < nj; ++i) jobs.j[i] = all[first + i];
+    // CTAs per job proportional to the bytes it streams (largest-remainder rounding so that every SM gets a CTA)
+    int wsum = 0;
+    for (int i = 0; i < nj; ++i) wsum += weight[first + i];
+    int cnt[tc::kDwMaxJobs], rem[tc::kDwMaxJobs], used = 0;
+    for (int i = 0; i < nj; ++i) {
+      const long long x = (long long)S->num_sms * weight[first + i];
+      cnt[i] = std::max(1, (int)(x / wsum));
+      rem[i] = (int)(x % wsum);
+      used += cnt[i];
+    }
+    while (used < S->num_sms) {
+      int best = 0;
+      for (int i = 1; i < nj; ++i) if (rem[i] > rem[best]) best = i;
+      cnt[best]++; rem[best] = -1; used++;
+    }
+    int begin = 0;
+    for (int i = 0; i < nj; ++i) {
+      const int per = std::max((int)round_up((rows + cnt[i] - 1) / cnt[i], 64), 64);
+      jobs.j[i].rows_per_cta = per;
+      jobs.j[i].cta_begin = begin;
+      jobs.j[i].cta_count = (rows + per - 1) / per;          // (<= cnt[i]; trailing CTAs of the range would have no rows)
+      begin += jobs.j[i].cta_count;
+    }
+    const int smem = tc::kDwStages * 8 * tc::kDwSlab + 256 + 1024;
+    ProfScope prof(h, st, MARF_PROF_DW);
+    launch_k(tc::k_tc_dw, begin, tc::kDwThreads, smem, st, jobs);
+    BF_LAUNCH(h);
   }
-  while (used < S->num_sms) {
-    int best = 0;
-    for (int i = 1; i < nj; ++i) if (rem[i] > rem[best]) best = i;
-    cnt[best]++; rem[best] = -1; used++;
-  }
-  int begin = 0;
-  for (int i = 0; i < nj; ++i) {
-    const int per = std::max((int)round_up((rows + cnt[i] - 1) / cnt[i], 64), 64);
-    jobs.j[i].rows_per_cta = per;
-    jobs.j[i].cta_begin = begin;
-    jobs.j[i].cta_count = (rows + per - 1) / per;          // (<= cnt[i]; trailing CTAs of the range would have no rows)
-    begin += jobs.j[i].cta_count;
-  }
-  const int smem = tc::kDwStages * 8 * tc::kDwSlab + 256 + 1024;
-  ProfScope prof(h, st, MARF_PROF_DW);
-  launch_k(tc::k_tc_dw, begin, tc::kDwThreads, smem, st, jobs);
-  BF_LAUNCH(h);
   return MARF_OK;
 }
 

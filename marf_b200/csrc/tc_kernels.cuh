@@ -436,8 +436,9 @@ struct DwJob {
   int rows_per_cta;     // multiple of 64
   int cta_begin, cta_count;   // CTAs [cta_begin, cta_begin + cta_count) of the launch split this job's pixel rows
   int n_tile;           // input columns of this job's tile: 64 or 256 (the MMA N)
-  int m_halves;         // ceil(out / 128)
-  int m_valid;          // out features
+  int m0;               // first output feature of this job (outputs wider than 256 are split over jobs)
+  int m_halves;         // 128-row halves of dY^T in this job (1 or 2)
+  int m_valid;          // out features of the layer
   int n_valid;          // in features
   int n0;               // first input column of this job's N tile
   int ld_w;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
           mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
           uint8_t* st = smem + s * stage_stride;
           const int row = row_begin + it * kDwRows;
-          for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &J.tmDY, i * 64, row, &full[s]);
+          for (int i = 0; i < a_slabs; ++i) tma_load_2d(st + i * kDwSlab, &J.tmDY, J.m0 + i * 64, row, &full[s]);
           for (int i = 0; i < b_slabs; ++i) tma_load_2d(st + (a_slabs + i) * kDwSlab, &J.tmX, J.n0 + i * 64, row, &full[s]);
         }
       }
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
         if (lane == 0) mbar_arrive(&empty[s]);
       }
       if (bias_warp) {
-        const int col = q * 64 + lane * 2;
+        const int col = J.m0 + q * 64 + lane * 2;
         if (col < J.m_valid) atomicAdd(&J.db[col], bs0);
         if (col + 1 < J.m_valid) atomicAdd(&J.db[col + 1], bs1);
       }
@@ -561,7 +562,7 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
       mbar_wait(done, 0);
       tc_fence_after();
       for (int mh = 0; mh < J.m_halves; ++mh) {
-        const int m = mh * 128 + r;
+        const int m = J.m0 + mh * 128 + r;
 #pragma unroll 1
         for (int c0 = 0; c0 < n_tile; c0 += 32) {
           uint32_t v[32];

@@ -26,6 +26,9 @@ STEP_CASES = {
     "mid_mask": dict(MID, use_masks=True),
     "mid_mask_c2f": dict(MID, use_masks=True, barf_c2f=(0.0, 0.4)),
     "mid_nomask_edges": dict(MID, use_masks=False, use_edges=True),
+    # no golden file (oracle-only cases: the oracle itself is pinned by the goldens of the cases above)
+    "wide512_L10": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10),
+    "wide512_c2f": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10, barf_c2f=(0.0, 0.4)),
     "implicit": dict(FULL2, use_masks=True, use_implicit_mask=True),
     "implicit_edges": dict(FULL2, use_masks=True, use_implicit_mask=True, use_edges=True),
 }
@@ -61,6 +64,9 @@ def build_case(name):
         params.mask_w, params.mask_b = fx.synth_mlp(seed_w + 1, mshapes)
         params.embed = fx.synth_embed(seed_w + 2, 1500, 128)
     images = make_images(cfg, seed_im)
+    if not os.path.exists(os.path.join(GOLDEN, "step_" + name + ".npz")):
+        it = 450                                               # oracle-only case (the iteration gen_golden.py uses for MID)
+        return cfg, params, images, it, it / cfg.max_iter, None
     g = load_golden("step_" + name)
     return cfg, params, images, int(g["it"]), float(g["progress"]), g
 

@@ -14,7 +14,8 @@ OUT_TOL = 2e-2
 LOSS_RTOL = 2e-2
 GRAD_L2 = 1.5e-1
 
-BF16_CASES = ["mid_mask", "mid_mask_c2f", "mid_nomask_edges", "implicit", "implicit_edges"]
+BF16_CASES = ["mid_mask", "mid_mask_c2f", "mid_nomask_edges", "implicit", "implicit_edges",
+              "wide512_L10", "wide512_c2f"]      # (BASELINE config 5's network: 4x512, posenc L=10, per-layer tensor-core kernels)
 
 
 def _named(params, grads, cfg):
