@@ -1361,7 +1361,39 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   return unpack_all(h, st, io);
 }
 
+// Several chunks and a normaliser that does not depend on the forward pass (no masks / disk masks: the mask head is the
+// only consumer of forward-dependent coefficients): forward + backward chunk by chunk in ONE sweep.  The generic path
+// (bf16_forward over all chunks for the statistics, then bf16_backward re-running the forward of every chunk because only one
+// chunk's activations are resident) costs a second forward pass.
+static int bf16_step_sweep(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+  const marf_config& c = h->cfg;
+  int rc = engine_begin_step(h, io, st, false);
+  if (rc) return rc;
+  rc = pack_all(h, st, io);
+  if (rc) return rc;
+  BF_TRY(h, cudaMemsetAsync(io->loss_sums, 0, MARF_N_SUMS * sizeof(double), st));
+  rc = engine_begin_backward(h, io, st);
+  if (rc) return rc;
+  launch_k(k_loss_coef_static, 1, 1, 0, st, h->sums_static, c.mask_mode, io->norm_rgb, h->n_local, h->coef);
+  BF_LAUNCH(h);
+  for (int ci = 0; ci < h->n_chunks; ++ci) {
+    rc = bf_forward_chunk(h, io, st, ci, true);
+    if (rc) return rc;
+    rc = bf_backward_chunk(h, io, st, ci);
+    if (rc) return rc;
+  }
+  if (c.use_edges) {                                   // (loss value only: without the mask head the edge term has no gradient)
+    rc = engine_edge_pass(h, io, st);
+    if (rc) return rc;
+  }
+  h->acts_valid = false;
+  rc = engine_finish_backward(h, io, st, false);
+  if (rc) return rc;
+  return unpack_all(h, st, io);
+}
+
 int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+  if (h->n_chunks > 1 && h->cfg.mask_mode != MARF_MASK_IMPLICIT && !getenv("MARF_NO_SWEEP")) return bf16_step_sweep(h, io, st);
   int rc = bf16_forward(h, io, st);
   if (rc) return rc;
   return bf16_backward(h, io, st);

@@ -612,6 +612,18 @@ static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_
   *out = c;
 }
 
+// the same when the rgb normaliser does not depend on the forward pass (no masks / disk masks): from the static mask sum
+// (or the host-supplied global one), so that a multi-chunk step can run forward + backward chunk by chunk in one sweep
+static __global__ void k_loss_coef_static(const double* __restrict__ sums_static, int mask_mode, double norm_rgb_host,
+                                          long long n_local, LossCoef* __restrict__ out) {
+  pdl_wait();
+  const double n_rgb = norm_rgb_host > 0 ? norm_rgb_host : (mask_mode == MARF_MASK_DISK ? sums_static[0] : 3.0 * (double)n_local);
+  LossCoef c;
+  c.inv_n_rgb = 1.0 / n_rgb;
+  c.s_over_n2 = 0.0; c.inv_n_mask = 0.0; c.inv_n_edge = 0.0; c.se_over_n2 = 0.0;     // (only the mask head's gradient uses them)
+  *out = c;
+}
+
 struct GradArgs {
   LossArgs l;
   float c_rgb, c_mask, c_edge;
