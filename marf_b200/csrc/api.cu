@@ -442,16 +442,23 @@ static int edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const marf_config& c = h->cfg;
   const float* pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
   double* ep = io->edge_pred ? io->edge_pred : h->edge_pred;
-  const dim3 eg((unsigned)((c.rows * h->w + 255) / 256), (unsigned)(c.batch * 3));     // x: one plane, y: image * 3 + channel
-  launch_k(k_sobel_mag, eg, 256, 0, st, pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
-  LAUNCH_CHECK(h);
-  launch_k(k_gauss5, eg, 256, 0, st, h->edge_mag, c.batch * 3, c.rows, h->w, ep);
-  LAUNCH_CHECK(h);
   EdgeArgs e;
   e.mask_mode = c.mask_mode;
   e.edge_pred = ep; e.edge_label = io->edges; e.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   e.masks_eroded = io->masks_eroded;
   e.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
+  if (c.rows >= 8 && h->w >= 8 && c.batch <= 65535 && !getenv("MARF_EDGE_SPLIT")) {
+    // Sobel -> Gauss -> statistics in one launch (the reflected window positions stay inside a block's window for images >= 8x8)
+    const dim3 ef((unsigned)((h->w + kEfW - 1) / kEfW), (unsigned)((c.rows + kEfH - 1) / kEfH), (unsigned)c.batch);
+    launch_k(k_edge_fused, ef, 256, 0, st, pred, c.rows, h->w, e, ep, io->loss_sums);
+    LAUNCH_CHECK(h);
+    return MARF_OK;
+  }
+  const dim3 eg((unsigned)((c.rows * h->w + 255) / 256), (unsigned)(c.batch * 3));     // x: one plane, y: image * 3 + channel
+  launch_k(k_sobel_mag, eg, 256, 0, st, pred, c.batch, 3, c.rows, h->w, 1, h->edge_mag);
+  LAUNCH_CHECK(h);
+  launch_k(k_gauss5, eg, 256, 0, st, h->edge_mag, c.batch * 3, c.rows, h->w, ep);
+  LAUNCH_CHECK(h);
   launch_k(k_edge_stats, (unsigned)std::min<long long>((h->n_local + 255) / 256, 592), 256, 0, st, h->geo, h->n_local, e, io->loss_sums);
   LAUNCH_CHECK(h);
   return MARF_OK;
@@ -475,6 +482,7 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   // so it is written after the image chain has consumed dYa (two launches of the same kernel).
   ga.dmlogits = nullptr; ga.dmld = 0;
   ga.dl_bf16 = nullptr; ga.dml_bf16 = nullptr;
+  ga.sums = nullptr; ga.norm_rgb = 0; ga.norm_edge = 0; ga.use_edges = 0;      // (fp32 path: coefficients from k_loss_coef)
   launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
   LAUNCH_CHECK(h);
   float* dx0 = nullptr;

@@ -1263,7 +1263,8 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
   return MARF_OK;
 }
 
-static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st, int ci) {
+// coef == nullptr: k_loss_grad resolves the loss coefficients itself from the (all-reduced) sums of the forward pass
+static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st, int ci, const LossCoef* coef = nullptr) {
   Bf16State* S = h->bf16;
   const marf_config& c = h->cfg;
   PxRange rg = bf_chunk(h, ci);
@@ -1280,7 +1281,8 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.dmlogits = implicit ? S->msk.dlogits : nullptr; ga.dmld = 4;
   ga.dl_bf16 = S->img.dl16;
   ga.dml_bf16 = implicit ? S->msk.dl16 : nullptr;
-  launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, h->coef);
+  ga.sums = io->loss_sums; ga.norm_rgb = io->norm_rgb; ga.norm_edge = io->norm_edge; ga.use_edges = c.use_edges;
+  launch_k(k_loss_grad, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, ga, coef);
   BF_LAUNCH(h);
   BfChain* c_img[1] = {&S->img};
   BfChain* c_msk[1] = {&S->msk};
@@ -1336,8 +1338,6 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const marf_config& c = h->cfg;
   int rc = engine_begin_backward(h, io, st);
   if (rc) return rc;
-  launch_k(k_loss_coef, 1, 1, 0, st, io->loss_sums, io->norm_rgb, io->norm_edge, c.use_edges, h->coef);
-  BF_LAUNCH(h);
   const bool implicit = c.mask_mode == MARF_MASK_IMPLICIT;
   if (implicit) BF_TRY(h, cudaMemsetAsync(h->bf16->msk.dW0x, 0, 256 * 64 * sizeof(float), st));
   for (int ci = 0; ci < h->n_chunks; ++ci) {
@@ -1379,7 +1379,7 @@ static int bf16_step_sweep(marf_handle* h, const marf_step_io* io, cudaStream_t 
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     rc = bf_forward_chunk(h, io, st, ci, true);
     if (rc) return rc;
-    rc = bf_backward_chunk(h, io, st, ci);
+    rc = bf_backward_chunk(h, io, st, ci, h->coef);
     if (rc) return rc;
   }
   if (c.use_edges) {                                   // (loss value only: without the mask head the edge term has no gradient)

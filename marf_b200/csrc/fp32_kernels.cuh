@@ -598,9 +598,8 @@ static __global__ void k_edge_stats(Geo g, long long n_total, EdgeArgs a, double
 }
 
 // resolve normalisers on device (after an optional all-reduce of `sums`): no host round trip
-static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
-                            int use_edges, LossCoef* __restrict__ out) {
-  pdl_wait();
+__device__ __forceinline__ LossCoef make_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
+                                                   int use_edges) {
   double n_rgb = norm_rgb_host > 0 ? norm_rgb_host : sums[MARF_N_RGB];
   double n_edge = norm_edge_host > 0 ? norm_edge_host : sums[MARF_N_EDGE];
   LossCoef c;
@@ -609,7 +608,12 @@ static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_
   c.inv_n_mask = sums[MARF_N_MASK] > 0 ? 1.0 / sums[MARF_N_MASK] : 0.0;
   c.inv_n_edge = (use_edges && n_edge > 0) ? 1.0 / n_edge : 0.0;
   c.se_over_n2 = (use_edges && n_edge > 0) ? 3.0 * sums[MARF_S_EDGE] / (n_edge * n_edge) : 0.0;
-  *out = c;
+  return c;
+}
+static __global__ void k_loss_coef(const double* __restrict__ sums, double norm_rgb_host, double norm_edge_host,
+                            int use_edges, LossCoef* __restrict__ out) {
+  pdl_wait();
+  *out = make_loss_coef(sums, norm_rgb_host, norm_edge_host, use_edges);
 }
 
 // the same when the rgb normaliser does not depend on the forward pass (no masks / disk masks): from the static mask sum
@@ -635,6 +639,8 @@ struct GradArgs {
   __nv_bfloat16* dl_bf16;      // optional bf16 copies [n_pad, 8] for the tensor-core dX / dW of the output layers (the TMA
                                // boxes over them are 64 columns wide: columns >= 8 are out-of-bounds zero fill, not HBM reads)
   __nv_bfloat16* dml_bf16;
+  // when the kernel is given no precomputed LossCoef it resolves the coefficients itself from the (all-reduced) sums
+  const double* sums; double norm_rgb, norm_edge; int use_edges;
 };
 
 static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef* __restrict__ coefp) {
@@ -652,7 +658,7 @@ static __global__ void k_loss_grad(Geo g, PxRange rg, GradArgs a, const LossCoef
     if (dmb) dmb[0] = make_uint4(0u, 0u, 0u, 0u);
     return;
   }
-  const LossCoef cf = *coefp;
+  const LossCoef cf = coefp ? *coefp : make_loss_coef(a.sums, a.norm_rgb, a.norm_edge, a.use_edges);
   long long i = rg.first + t;
   long long per = (long long)g.rows * g.w;
   long long b = i / per, rem = i - b * per;
@@ -741,6 +747,77 @@ static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch,
       gy += d[dy] * s[dx] * v;
     }
   mag[i] = sqrt(gx * gx + gy * gy);
+}
+
+// Sobel magnitude -> 5x5 Gaussian -> edge statistics of one step in ONE launch (replaces k_sobel_mag + k_gauss5 + k_edge_stats
+// on the training path; same fp64 operation order, so the results are bit-identical).  Block = 32x8 output pixels of one
+// image; per channel: the 38x14 input window (REFLECT_101 resolved while loading) and the 36x12 magnitude window live in SMEM.
+// A magnitude outside the image is the magnitude AT the reflected position, as OpenCV's two-pass evaluation gives.
+constexpr int kEfW = 32, kEfH = 8;
+static __global__ void __launch_bounds__(256) k_edge_fused(const float* __restrict__ pred /* [batch, rows*w, 3] */, int rows, int w, EdgeArgs a,
+                                                           double* __restrict__ edge_out /* [batch,3,rows,w] */,
+                                                           double* __restrict__ sums) {
+  pdl_wait();
+  __shared__ double s_in[kEfH + 6][kEfW + 6];
+  __shared__ double s_mag[kEfH + 4][kEfW + 4];
+  __shared__ double red[32];
+  const int b = blockIdx.z, x0 = blockIdx.x * kEfW, y0 = blockIdx.y * kEfH;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int x = x0 + tx, y = y0 + ty;
+  const bool inside = x < w && y < rows;
+  const long long per = (long long)rows * w;
+  const long long pix = (long long)y * w + x;
+  double m = 1.0;
+  if (inside) {
+    if (a.mask_mode == MARF_MASK_DISK) m = (double)a.masks_eroded[b * per + pix];
+    else if (a.mask_mode == MARF_MASK_IMPLICIT) m = (double)a.mask_pred[b * per + pix];
+  }
+  double s_acc = 0.0;
+  const double sk[3] = {1, 2, 1}, dk[3] = {-1, 0, 1};
+  const double g5[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
+  for (int c = 0; c < 3; ++c) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kEfH + 6) * (kEfW + 6); i += 256) {
+      const int iy = i / (kEfW + 6), ix = i - iy * (kEfW + 6);
+      const int yy = reflect101(y0 - 3 + iy, rows), xx = reflect101(x0 - 3 + ix, w);
+      s_in[iy][ix] = (double)pred[((long long)b * per + (long long)yy * w + xx) * 3 + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < (kEfH + 4) * (kEfW + 4); i += 256) {
+      const int my = i / (kEfW + 4), mx = i - my * (kEfW + 4);
+      // magnitude at the reflected position q of window coordinate p; q's neighbours are within the loaded window
+      const int qy = reflect101(y0 - 2 + my, rows) - (y0 - 3), qx = reflect101(x0 - 2 + mx, w) - (x0 - 3);
+      double gx = 0, gy = 0;
+      if (qy >= 1 && qy <= kEfH + 4 && qx >= 1 && qx <= kEfW + 4) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const double v = s_in[qy + dy - 1][qx + dx - 1];
+            gx += sk[dy] * dk[dx] * v;
+            gy += dk[dy] * sk[dx] * v;
+          }
+      }
+      s_mag[my][mx] = sqrt(gx * gx + gy * gy);
+    }
+    __syncthreads();
+    if (inside) {
+      double acc = 0;
+#pragma unroll
+      for (int dy = 0; dy < 5; ++dy) {
+        double rowacc = 0;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) rowacc += g5[dx] * s_mag[ty + dy][tx + dx];
+        acc += g5[dy] * rowacc;
+      }
+      edge_out[((long long)b * 3 + c) * per + pix] = acc;
+      const double l = a.edge_label[((long long)b * a.label_channels + (a.label_channels == 1 ? 0 : c)) * per + pix];
+      const double d = (acc - l) * m;
+      s_acc += d * d;
+    }
+  }
+  block_sum_atomic(s_acc, &sums[MARF_S_EDGE], red);
+  block_sum_atomic(inside ? 3.0 * m : 0.0, &sums[MARF_N_EDGE], red);
 }
 
 static __global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {

@@ -109,7 +109,6 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
   constexpr int kGroup = 2 * CL;                                        // tiles per work item
   const int n_pairs = (jobs.n_tiles + kGroup - 1) / kGroup;             // work items per chain
   const int n_items = n_pairs * jobs.n;
-  constexpr uint32_t kWBytes = kChWStage / CL;                          // this CTA's share of a weight chunk
 
   if (threadIdx.x == 0) {
     for (int c = 0; c < jobs.n; ++c) {
