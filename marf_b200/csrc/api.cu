@@ -501,7 +501,7 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   return MARF_OK;
 }
 
-static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32 = true) {
+static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32 = true, bool sl3 = true) {
   CUDA_TRY(h, cudaSetDevice(h->cfg.device));
   int rc = refresh_data(h, io, st);
   if (rc) return rc;
@@ -514,8 +514,10 @@ static int begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, b
       if (rc) return rc;
     }
   }
-  launch_k(k_sl3_to_SL3, h->cfg.batch_global, 64, 0, st, io->warp, h->cfg.batch_global, h->Hm);
-  LAUNCH_CHECK(h);
+  if (sl3) {
+    launch_k(k_sl3_to_SL3, h->cfg.batch_global, 64, 0, st, io->warp, h->cfg.batch_global, h->Hm);
+    LAUNCH_CHECK(h);
+  }
   return MARF_OK;
 }
 
@@ -541,7 +543,7 @@ static int finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t 
 }
 
 namespace marf {
-int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32) { return begin_step(h, io, st, pack_fp32); }
+int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32, bool sl3) { return begin_step(h, io, st, pack_fp32, sl3); }
 int engine_edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return edge_pass(h, io, st); }
 int engine_begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return begin_backward(h, io, st, nullptr); }
 int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack) { return finish_backward(h, io, st, unpack); }

@@ -159,10 +159,10 @@ __global__ void k_mask_uv_cls(Geo g, PxRange rg, const float* __restrict__ rgb, 
 
 // T[c][j] = b0[j] + sum_ch sum_e W0[j][ch*E + e] * embed[bit_ch(c)][e], one warp per (class, output) pair, written as
 // bf16 hi / lo halves into columns k_uv + c and k_uv + 8 + c of the packed forward weights Wk [256, 64] of layer 0
-__global__ void k_mask_table(const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ embed,
-                             int k_in, int k_out, int edim, int k_uv, bf16* __restrict__ Wk, int ldk) {
-  pdl_wait();
-  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void mask_table_block(int vblock, const float* __restrict__ W0, const float* __restrict__ b0,
+                                                 const float* __restrict__ embed, int k_in, int k_out, int edim, int k_uv,
+                                                 bf16* __restrict__ Wk, int ldk) {
+  const int gw = (vblock * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= 8 * k_out) return;
   const int c = gw / k_out, j = gw - c * k_out;
   const float* w = W0 + (size_t)j * k_in;
@@ -175,6 +175,11 @@ __global__ void k_mask_table(const float* __restrict__ W0, const float* __restri
     Wk[(size_t)j * ldk + k_uv + c] = hi;
     Wk[(size_t)j * ldk + k_uv + 8 + c] = __float2bfloat16(t - __bfloat162float(hi));
   }
+}
+__global__ void k_mask_table(const float* __restrict__ W0, const float* __restrict__ b0, const float* __restrict__ embed,
+                             int k_in, int k_out, int edim, int k_uv, bf16* __restrict__ Wk, int ldk) {
+  pdl_wait();
+  mask_table_block(blockIdx.x, W0, b0, embed, k_in, k_out, edim, k_uv, Wk, ldk);
 }
 
 // Layer-0 gradient of the mask head from the dW tile X = dY0^T [uv | onehot | onehot] ([k_out, 64] fp32):
@@ -385,15 +390,51 @@ static __global__ void k_bf16_to_f32(long long n, const bf16* __restrict__ in, f
 }
 
 // table-driven (un)packing: one launch for every layer of both networks
-struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode, src_ld, col_off; };   // mode 0: f32 pad, 1: bf16, 2: bf16 transposed, 3: bf16 hi rows [0,8) / lo rows [8,16)
-constexpr int kMaxPack = 48;
-struct PackTable { PackEntry e[kMaxPack]; int n; };
+// mode 0: f32 pad, 1: bf16, 2: bf16 transposed, 3: bf16 hi rows [0,8) / lo rows [8,16); wcols > 0: only columns < wcols are written
+struct PackEntry { const float* src; void* dst; int rows, cols, prow, pcol, mode, src_ld, col_off, wcols; };
+constexpr int kMaxPack = 40;
+// The prologue of a step in ONE launch: rows [0, n) of the grid pack the weights (table-driven); when `fused` the three rows
+// after them compute the homographies H = exp(A(h)) of all patches, the mask head's colour-class table, and zero the
+// accumulators of the step (gradient twins, per-patch Jacobians, class-table scratch, loss sums).
+struct PackTable {
+  PackEntry e[kMaxPack]; int n;
+  int fused;
+  const float* warp; int n_patches; float* Hm;                                            // row n
+  const float* mW0; const float* mb0; const float* embed; int mk_in, mk_out, edim, k_uv; bf16* mWk; int mldk;   // row n+1 (mk_out == 0: none)
+  void* zptr[5]; unsigned long long zbytes[5];                                            // row n+2 (8-byte multiples)
+};
 static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
   pdl_wait();
+  if ((int)blockIdx.y >= t.n) {
+    const int role = (int)blockIdx.y - t.n;
+    if (role == 0) {
+      __shared__ double X[9], T[9], R[9];
+      for (int b = blockIdx.x; b < t.n_patches; b += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x == 0) sl3_generator(t.warp + 8 * b, X);
+        __syncthreads();
+        expm_coop<3>(X, T, R, threadIdx.x);
+        if (threadIdx.x < 9) t.Hm[9 * b + threadIdx.x] = (float)R[threadIdx.x];
+      }
+    } else if (role == 1) {
+      const int nvb = (8 * t.mk_out * 32 + (int)blockDim.x - 1) / (int)blockDim.x;
+      for (int vb = blockIdx.x; vb < nvb; vb += gridDim.x)
+        mask_table_block(vb, t.mW0, t.mb0, t.embed, t.mk_in, t.mk_out, t.edim, t.k_uv, t.mWk, t.mldk);
+    } else {
+      for (int z = 0; z < 5; ++z) {
+        unsigned long long* p = reinterpret_cast<unsigned long long*>(t.zptr[z]);
+        const unsigned long long n8 = t.zbytes[z] / 8;
+        for (unsigned long long i = blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (unsigned long long)gridDim.x * blockDim.x)
+          p[i] = 0ull;
+      }
+    }
+    return;
+  }
   const PackEntry& E = t.e[blockIdx.y];
   const int tot = E.prow * E.pcol;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
     int pr = i / E.pcol, pc = i - pr * E.pcol;
+    if (E.wcols > 0 && pc >= E.wcols) continue;
     int r = E.mode == 2 ? pc : pr, c = E.mode == 2 ? pr : pc;
     if (E.mode == 3) r = pr & 7;
     float v = (r < E.rows && c < E.cols) ? E.src[(size_t)r * E.src_ld + E.col_off + c] : 0.f;
@@ -402,15 +443,45 @@ static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
     else reinterpret_cast<bf16*>(E.dst)[i] = __float2bfloat16(v);
   }
 }
-struct UnpackEntry { const float* src; float* dst; int rows, cols, pcol; };
-struct UnpackTable { UnpackEntry e[kMaxPack]; int n; };
+// The tail of the backward pass in ONE launch: every gradient from its padded fp32 twin to the caller's tensor (mode 0), the
+// mask head's layer-0 weight / bias gradients straight from the class-table scratch (modes 1 / 2: what k_mask_dw_finalize
+// computes, without the round trip through the padded twin), and — row t.n of the grid — the sl(3) adjoint of every owned
+// patch plus the zero rows of the patches other ranks own.
+struct UnpackEntry { const float* src; float* dst; int rows, cols, pcol; int mode; const float* embed; int edim, k_uv; };
+struct UnpackTable {
+  UnpackEntry e[kMaxPack]; int n;
+  const float* warp; const double* G; float* g_warp; int patch_offset, n_local, n_global;     // sl(3) row (g_warp == nullptr: none)
+};
 static __global__ void k_unpack_table(const __grid_constant__ UnpackTable t) {
   pdl_wait();
+  if ((int)blockIdx.y == t.n) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < t.n_global * 8; b += gridDim.x * blockDim.x) {
+      const int p = b >> 3;
+      if (p < t.patch_offset || p >= t.patch_offset + t.n_local) t.g_warp[b] = 0.f;
+    }
+    for (int bl = blockIdx.x; bl < t.n_local; bl += gridDim.x) sl3_backward_block(t.warp, t.G, t.patch_offset, bl, t.g_warp);
+    return;
+  }
   const UnpackEntry& E = t.e[blockIdx.y];
   const int tot = E.rows * E.cols;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) {
     int r = i / E.cols, c = i - r * E.cols;
-    E.dst[i] = E.src[(size_t)r * E.pcol + c];
+    if (E.mode == 0) {
+      E.dst[i] = E.src[(size_t)r * E.pcol + c];
+    } else {
+      // src = X [k_out, 64] = dY0^T [uv | onehot | onehot]: uv columns -> dW0[:, 3E : 3E + k_uv]; per-class sums S[c] = X[r][k_uv + c]
+      const float* x = E.src + (size_t)(E.mode == 1 ? r : c) * 64;
+      float s0 = 0.f, s1 = 0.f;
+      const int ch = E.mode == 1 && c < 3 * E.edim ? c / E.edim : 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float v = x[E.k_uv + k];
+        if ((k >> ch) & 1) s1 += v; else s0 += v;
+      }
+      if (E.mode == 2) E.dst[i] = s0 + s1;                                     // db0[j] = sum over the classes
+      else if (c >= 3 * E.edim) E.dst[i] = x[c - 3 * E.edim];                  // uv columns
+      else E.dst[i] = s0 * E.embed[c - ch * E.edim] + s1 * E.embed[E.edim + c - ch * E.edim];
+    }
   }
 }
 
@@ -464,6 +535,7 @@ struct Bf16State {
   BfChain img, msk;
   float* dX0 = nullptr;                   // [chunk, 64] fp32
   int num_sms = 148;
+  bool table_done = false;                // the class table of this step was written by the fused prologue launch
   uint32_t* flags_all = nullptr;          // every per-tile flag array of both chains, zeroed before each chained launch
   size_t flags_words = 0, flags_used = 0;
 };
@@ -1126,15 +1198,24 @@ static int thin_bwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const
 }
 
 // one launch: bias (fp32) + bf16 forward / transposed weights of every tensor-core layer
-static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
+static size_t chain_twin_floats(const Chain& C) {       // the padded fp32 gradient twins of a chain are one allocation
+  size_t t = 0;
+  for (int l = 0; l < C.n; ++l) t += (size_t)C.ld_out[l] * C.ld_in[l] + C.ld_out[l];
+  return t;
+}
+
+// fused: the launch also computes the homographies and the mask head's class table and zeroes the step's accumulators
+// (single-call marf_step); otherwise those stay separate launches / memsets (two-phase entry points, multi-chunk sweeps)
+static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io, bool fused = false) {
   Bf16State* S = h->bf16;
-  PackTable t;
+  PackTable t{};
   t.n = 0;
   int max_tot = 0;
-  auto add = [&](const float* src, void* dst, int rows, int cols, int prow, int pcol, int mode, int src_ld = -1, int col_off = 0) {
+  auto add = [&](const float* src, void* dst, int rows, int cols, int prow, int pcol, int mode, int src_ld = -1, int col_off = 0,
+                 int wcols = 0) {
     PackEntry& e = t.e[t.n++];
     e.src = src; e.dst = dst; e.rows = rows; e.cols = cols; e.prow = prow; e.pcol = pcol; e.mode = mode;
-    e.src_ld = src_ld < 0 ? cols : src_ld; e.col_off = col_off;
+    e.src_ld = src_ld < 0 ? cols : src_ld; e.col_off = col_off; e.wcols = wcols;
     max_tot = std::max(max_tot, prow * pcol);
   };
   BfChain* chains[2] = {&S->img, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? &S->msk : nullptr};
@@ -1153,11 +1234,27 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
       if (B.L[l].thin) continue;
       // (layer 0 of the mask head only multiplies the uv columns: a window of the caller's [k_out, k_in] matrix)
       const int off = l == 0 ? B.col_off0 : 0;
-      add(Ws[ci][l], B.L[l].Wk, B.L[l].k_out, B.L[l].k_in, B.L[l].np, B.L[l].kp, 1, F.k_in[l], off);
+      // (class-table mode: columns >= k_in of Wk belong to the table k_mask_table / the fused prologue writes: never touched here)
+      add(Ws[ci][l], B.L[l].Wk, B.L[l].k_out, B.L[l].k_in, B.L[l].np, B.L[l].kp, 1, F.k_in[l], off, off > 0 ? B.L[l].k_in : 0);
       add(Ws[ci][l], B.L[l].Wt, B.L[l].k_out, B.L[l].k_in, B.L[l].kp, B.L[l].np, 2, F.k_in[l], off);
     }
   }
-  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
+  const bool implicit = h->cfg.mask_mode == MARF_MASK_IMPLICIT;
+  t.fused = fused ? 1 : 0;
+  if (fused) {
+    t.warp = io->warp; t.n_patches = h->cfg.batch_global; t.Hm = h->Hm;
+    if (implicit) {
+      t.mW0 = io->mask_w[0]; t.mb0 = io->mask_b[0]; t.embed = io->embed; t.mk_in = h->msk.k_in[0]; t.mk_out = h->msk.k_out[0];
+      t.edim = h->cfg.mask_embed_dim; t.k_uv = S->msk.L[0].k_in; t.mWk = S->msk.L[0].Wk; t.mldk = S->msk.L[0].kp;
+    }
+    int z = 0;
+    t.zptr[z] = h->img.gWp[0]; t.zbytes[z++] = chain_twin_floats(h->img) * sizeof(float);
+    if (implicit) { t.zptr[z] = h->msk.gWp[0]; t.zbytes[z++] = chain_twin_floats(h->msk) * sizeof(float); }
+    t.zptr[z] = h->G; t.zbytes[z++] = (size_t)h->cfg.batch * 9 * sizeof(double);
+    if (implicit) { t.zptr[z] = S->msk.dW0x; t.zbytes[z++] = 256 * 64 * sizeof(float); }
+    t.zptr[z] = io->loss_sums; t.zbytes[z++] = MARF_N_SUMS * sizeof(double);
+  }
+  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n + (fused ? 3 : 0));
   launch_k(k_pack_table, grid, 256, 0, st, t);
   BF_LAUNCH(h);
   return MARF_OK;
@@ -1165,8 +1262,11 @@ static int pack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
 
 static int unpack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
   Bf16State* S = h->bf16;
-  UnpackTable t;
+  UnpackTable t{};
   t.n = 0;
+  if (!io->g_warp) return fail(h, MARF_ERR_INVALID, "missing g_warp");
+  t.warp = io->warp; t.G = h->G; t.g_warp = io->g_warp;
+  t.patch_offset = h->cfg.patch_offset; t.n_local = h->cfg.batch; t.n_global = h->cfg.batch_global;
   int max_tot = 0;
   BfChain* chains[2] = {&S->img, h->cfg.mask_mode == MARF_MASK_IMPLICIT ? &S->msk : nullptr};
   float* const* gW[2] = {io->g_mlp_w, io->g_mask_w};
@@ -1180,10 +1280,15 @@ static int unpack_all(marf_handle* h, cudaStream_t st, const marf_step_io* io) {
       a.src = F.gWp[l]; a.dst = gW[ci][l]; a.rows = F.k_out[l]; a.cols = F.k_in[l]; a.pcol = F.ld_in[l];
       UnpackEntry& b = t.e[t.n++];
       b.src = F.gbp[l]; b.dst = gb[ci][l]; b.rows = 1; b.cols = F.k_out[l]; b.pcol = F.ld_out[l];
+      if (l == 0 && chains[ci]->col_off0 > 0) {
+        // mask head layer 0 (class-table mode): from the [k_out, 64] scratch the dW launch accumulated
+        a.src = chains[ci]->dW0x; a.mode = 1; a.embed = io->embed; a.edim = h->cfg.mask_embed_dim; a.k_uv = chains[ci]->L[0].k_in;
+        b.src = chains[ci]->dW0x; b.mode = 2; b.embed = io->embed; b.edim = h->cfg.mask_embed_dim; b.k_uv = chains[ci]->L[0].k_in;
+      }
       max_tot = std::max(max_tot, F.k_out[l] * F.k_in[l]);
     }
   }
-  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n);
+  dim3 grid(std::min((max_tot + 255) / 256, 64), t.n + 1);
   launch_k(k_unpack_table, grid, 256, 0, st, t);
   BF_LAUNCH(h);
   return MARF_OK;
@@ -1224,9 +1329,11 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
       }
       h->feats_valid = h->n_chunks == 1;
     }
-    launch_k(k_mask_table, (8 * h->msk.k_out[0] * 32 + 255) / 256, 256, 0, st, io->mask_w[0], io->mask_b[0], io->embed,
-             h->msk.k_in[0], h->msk.k_out[0], c.mask_embed_dim, S->msk.L[0].k_in, S->msk.L[0].Wk, S->msk.L[0].kp);
-    BF_LAUNCH(h);
+    if (!S->table_done) {                         // (the fused prologue of a single-call step has already written it)
+      launch_k(k_mask_table, (8 * h->msk.k_out[0] * 32 + 255) / 256, 256, 0, st, io->mask_w[0], io->mask_b[0], io->embed,
+               h->msk.k_in[0], h->msk.k_out[0], c.mask_embed_dim, S->msk.L[0].k_in, S->msk.L[0].Wk, S->msk.L[0].kp);
+      BF_LAUNCH(h);
+    }
   }
   // chain after chain, each followed at once by its output layer: the last hidden activation is still in L2
   BfChain* c_img[1] = {&S->img};
@@ -1310,18 +1417,21 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
 }
 
 // shared with api.cu
-int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32);
+int engine_begin_step(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool pack_fp32, bool sl3 = true);
 int engine_edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st);
 int engine_begin_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st);
 int engine_finish_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool unpack);
 
-int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+// fused = the single-call step: one prologue launch packs the weights, computes H and the class table and zeroes every
+// accumulator of the step (forward AND backward), so that no memset node sits between the launches
+static int bf16_forward_impl(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool fused) {
   const marf_config& c = h->cfg;
-  int rc = engine_begin_step(h, io, st, false);   // H matrices, schedule, data caches
+  int rc = engine_begin_step(h, io, st, false, !fused);   // schedule, data caches (+ H matrices unless fused)
   if (rc) return rc;
-  rc = pack_all(h, st, io);
+  rc = pack_all(h, st, io, fused);
   if (rc) return rc;
-  BF_TRY(h, cudaMemsetAsync(io->loss_sums, 0, MARF_N_SUMS * sizeof(double), st));
+  h->bf16->table_done = fused;
+  if (!fused) BF_TRY(h, cudaMemsetAsync(io->loss_sums, 0, MARF_N_SUMS * sizeof(double), st));
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     rc = bf_forward_chunk(h, io, st, ci, true);
     if (rc) return rc;
@@ -1331,15 +1441,20 @@ int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
     if (rc) return rc;
   }
   h->acts_valid = h->n_chunks == 1;
+  h->bf16->table_done = false;
   return MARF_OK;
 }
+int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return bf16_forward_impl(h, io, st, false); }
 
-int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+static int bf16_backward_impl(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool fused) {
   const marf_config& c = h->cfg;
-  int rc = engine_begin_backward(h, io, st);
-  if (rc) return rc;
+  int rc = MARF_OK;
   const bool implicit = c.mask_mode == MARF_MASK_IMPLICIT;
-  if (implicit) BF_TRY(h, cudaMemsetAsync(h->bf16->msk.dW0x, 0, 256 * 64 * sizeof(float), st));
+  if (!fused) {
+    rc = engine_begin_backward(h, io, st);
+    if (rc) return rc;
+    if (implicit) BF_TRY(h, cudaMemsetAsync(h->bf16->msk.dW0x, 0, 256 * 64 * sizeof(float), st));
+  }
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     if (!h->acts_valid) {
       rc = bf_forward_chunk(h, io, st, ci, false);
@@ -1349,17 +1464,10 @@ int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
     if (rc) return rc;
   }
   h->acts_valid = false;
-  if (implicit) {
-    // colour columns of dW0 and db0 of the mask head from the per-class column sums of dY0 (all chunks)
-    const int tot = h->msk.k_out[0] * h->msk.k_in[0];
-    launch_k(k_mask_dw_finalize, (tot + 255) / 256, 256, 0, st, h->bf16->msk.dW0x, io->embed, c.mask_embed_dim, h->msk.k_out[0],
-             h->bf16->msk.L[0].k_in, h->msk.gWp[0], h->msk.ld_in[0], h->msk.gbp[0]);
-    BF_LAUNCH(h);
-  }
-  rc = engine_finish_backward(h, io, st, false);
-  if (rc) return rc;
+  // (mask head layer 0, the sl(3) adjoint and the hand-over of every gradient: one launch)
   return unpack_all(h, st, io);
 }
+int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return bf16_backward_impl(h, io, st, false); }
 
 // Several chunks and a normaliser that does not depend on the forward pass (no masks / disk masks: the mask head is the
 // only consumer of forward-dependent coefficients): forward + backward chunk by chunk in ONE sweep.  The generic path
@@ -1387,16 +1495,15 @@ static int bf16_step_sweep(marf_handle* h, const marf_step_io* io, cudaStream_t 
     if (rc) return rc;
   }
   h->acts_valid = false;
-  rc = engine_finish_backward(h, io, st, false);
-  if (rc) return rc;
   return unpack_all(h, st, io);
 }
 
 int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   if (h->n_chunks > 1 && h->cfg.mask_mode != MARF_MASK_IMPLICIT && !getenv("MARF_NO_SWEEP")) return bf16_step_sweep(h, io, st);
-  int rc = bf16_forward(h, io, st);
+  const bool fused = h->n_chunks == 1 && !getenv("MARF_NO_FUSED_PROLOGUE");
+  int rc = bf16_forward_impl(h, io, st, fused);
   if (rc) return rc;
-  return bf16_backward(h, io, st);
+  return bf16_backward_impl(h, io, st, fused);
 }
 
 }  // namespace marf

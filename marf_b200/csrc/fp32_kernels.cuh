@@ -112,13 +112,13 @@ static __global__ void k_sl3_to_SL3(const float* __restrict__ warp, int n, float
   if (tid < 9) out9[9 * b + tid] = (float)R[tid];
 }
 
-// G[b] = dL/dH (row-major 3x3, fp64) -> g_warp[b,8] (fp32, overwritten for owned patches); one block per patch
-static __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
-                               int n_local, float* __restrict__ g_warp) {
-  pdl_wait();
+// G[bl] = dL/dH (row-major 3x3, fp64) -> g_warp[bl + patch_offset, 8] (fp32); all threads of the block call it (>= 36 threads)
+static __device__ void sl3_backward_block(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset, int bl,
+                                   float* __restrict__ g_warp) {
   __shared__ double X[36], T[36], R[36];
-  const int bl = blockIdx.x, tid = threadIdx.x;
+  const int tid = threadIdx.x;
   const int b = bl + patch_offset;
+  __syncthreads();                                   // (the shared scratch may still be read by a previous call)
   if (tid == 0) {
     double A[9];
     sl3_generator(warp + 8 * b, A);
@@ -146,6 +146,14 @@ static __global__ void k_sl3_backward(const float* __restrict__ warp, const doub
     o[6] = (float)dA[6];            // h7 -> A20
     o[7] = (float)dA[7];            // h8 -> A21
   }
+}
+
+// one block per patch
+static __global__ void k_sl3_backward(const float* __restrict__ warp, const double* __restrict__ G, int patch_offset,
+                               int n_local, float* __restrict__ g_warp) {
+  pdl_wait();
+  (void)n_local;
+  sl3_backward_block(warp, G, patch_offset, blockIdx.x, g_warp);
 }
 
 // warped crop corners (warp.py:83-93): [(X0,Y0),(X0,Y1),(X1,Y1),(X1,Y0)]
