@@ -298,15 +298,16 @@ def run_marf(args):
     # Input prefetch, as a training data loader does it: the targets of step i+1 are copied host->device on a copy stream into
     # the second of two device buffers while step i computes (every step's H2D copy is inside the timed region; a buffer is
     # refilled only after the step that read it has finished).  The loss of every step is read back (D2H into pinned
-    # memory); the host consumes it one step later so that Python/launch overhead overlaps the GPU's work on the next step.
+    # memory); the host consumes it two steps later so that Python/launch overhead overlaps the GPU's work on the next steps.
     copy_st = torch.cuda.Stream(device=device)
     bufs = [loc.rgb, torch.empty_like(loc.rgb)]
     ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
     ev_free = [torch.cuda.Event(), torch.cuda.Event()]
     for ev in ev_free:
         ev.record(st)
-    loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
-    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    LAG = 2                                             # the host reads step i's loss while steps i+1, i+2 are queued
+    loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(LAG + 1)]
+    loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
     seen = []
 
     def prefetch(i):
@@ -323,11 +324,13 @@ def run_marf(args):
         ev_free[i & 1].record(st)
         if opt.warp.fix_first and m.fused_tail is None:
             g.warp_param.weight.data[0] = 0
-        loss_host[i & 1].copy_(loss.all.detach().reshape(1), non_blocking=True)   # D2H of the step's result
-        loss_ev[i & 1].record(st)
-        if i > 0:
-            loss_ev[(i - 1) & 1].synchronize()
-            seen.append(float(loss_host[(i - 1) & 1]))
+        k = i % (LAG + 1)
+        loss_host[k].copy_(loss.all.detach().reshape(1), non_blocking=True)       # D2H of the step's result
+        loss_ev[k].record(st)
+        if i >= LAG:
+            j = (i - LAG) % (LAG + 1)
+            loss_ev[j].synchronize()
+            seen.append(float(loss_host[j]))
 
     prefetch(0)
     for i in range(3):
@@ -379,7 +382,7 @@ def run_marf(args):
                     e2e=dict(value=e2e_value, unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                              ms_per_step=e2e_ms, what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first); every step's targets are copied "
                                   "from pinned host memory (prefetched on a copy stream during the previous step, double-buffered) and the "
-                                  "loss is read back every step (consumed one step later)"),
+                                  "loss is read back every step (consumed two steps later)"),
                     gpu_launches=launches)
         line.update(roofline_lines(wl, kern, pk, n_px_total // world, tflops, args))
         if args.gpus == 1 and not args.no_cpu:

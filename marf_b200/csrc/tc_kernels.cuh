@@ -569,10 +569,16 @@ __global__ void __launch_bounds__(kDwThreads, 1) k_tc_dw(const __grid_constant__
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mh * n_tile + c0, v);
           tmem_ld_wait();
           if (m < J.m_valid) {
+            // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 atomic operations of the scalar form;
+            // the ~16 CTAs of a job all add into the same [out, in] matrix at the end of the kernel, and that tail was 8 %
+            // of the launch.  ld_w is a multiple of 4 and columns up to the next multiple of 4 past n_valid are padding.
             float* o = J.dW + (size_t)m * J.ld_w + J.n0 + c0;
 #pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (J.n0 + c0 + e < J.n_valid) atomicAdd(o + e, __uint_as_float(v[e]));
+            for (int e = 0; e < 32; e += 4)
+              if (J.n0 + c0 + e < J.n_valid)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + e), "f"(__uint_as_float(v[e])),
+                             "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                             : "memory");
           }
         }
       }
