@@ -264,7 +264,8 @@ def run_marf(args):
         g.forward(var, mode="train")
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:                                       # (one nvidia-smi poller per job, not one per rank)
+        sampler.start()
     time.sleep(0.1)
     launches0 = g.engine.launches
     evs = []
