@@ -536,6 +536,7 @@ struct Bf16State {
   float* dX0 = nullptr;                   // [chunk, 64] fp32
   int num_sms = 148;
   bool table_done = false;                // the class table of this step was written by the fused prologue launch
+  bool accs_zeroed = false;               // the prologue launch of the forward pass already zeroed the backward accumulators
   uint32_t* flags_all = nullptr;          // every per-tile flag array of both chains, zeroed before each chained launch
   size_t flags_words = 0, flags_used = 0;
 };
@@ -1431,6 +1432,7 @@ static int bf16_forward_impl(marf_handle* h, const marf_step_io* io, cudaStream_
   rc = pack_all(h, st, io, fused);
   if (rc) return rc;
   h->bf16->table_done = fused;
+  h->bf16->accs_zeroed = fused;
   if (!fused) BF_TRY(h, cudaMemsetAsync(io->loss_sums, 0, MARF_N_SUMS * sizeof(double), st));
   for (int ci = 0; ci < h->n_chunks; ++ci) {
     rc = bf_forward_chunk(h, io, st, ci, true);
@@ -1444,7 +1446,11 @@ static int bf16_forward_impl(marf_handle* h, const marf_step_io* io, cudaStream_
   h->bf16->table_done = false;
   return MARF_OK;
 }
-int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return bf16_forward_impl(h, io, st, false); }
+// (two-phase entry points: the forward's prologue launch also zeroes what the backward pass accumulates into; the backward
+//  pass skips its memsets when it finds them done)
+int bf16_forward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+  return bf16_forward_impl(h, io, st, h->n_chunks == 1 && !getenv("MARF_NO_FUSED_PROLOGUE"));
+}
 
 static int bf16_backward_impl(marf_handle* h, const marf_step_io* io, cudaStream_t st, bool fused) {
   const marf_config& c = h->cfg;
@@ -1467,7 +1473,11 @@ static int bf16_backward_impl(marf_handle* h, const marf_step_io* io, cudaStream
   // (mask head layer 0, the sl(3) adjoint and the hand-over of every gradient: one launch)
   return unpack_all(h, st, io);
 }
-int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) { return bf16_backward_impl(h, io, st, false); }
+int bf16_backward(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
+  const bool zeroed = h->bf16->accs_zeroed;
+  h->bf16->accs_zeroed = false;
+  return bf16_backward_impl(h, io, st, zeroed);
+}
 
 // Several chunks and a normaliser that does not depend on the forward pass (no masks / disk masks: the mask head is the
 // only consumer of forward-dependent coefficients): forward + backward chunk by chunk in ONE sweep.  The generic path
@@ -1503,6 +1513,7 @@ int bf16_step(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   const bool fused = h->n_chunks == 1 && !getenv("MARF_NO_FUSED_PROLOGUE");
   int rc = bf16_forward_impl(h, io, st, fused);
   if (rc) return rc;
+  h->bf16->accs_zeroed = false;
   return bf16_backward_impl(h, io, st, fused);
 }
 
