@@ -107,3 +107,42 @@ def test_bf16_refuses_unsupported_widths_loudly():
     cfg, *_ = cases.build_case("small_mask")      # 64-wide MLP: not built for the tensor-core path
     with pytest.raises(L.MarfError, match="bf16"):
         gpu_util.make_engine(cfg, "bf16")
+
+
+def _run(name, monkeypatch, env, **kw):
+    import gpu_util
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cfg, params, images, it, progress, g = cases.build_case(name)
+    eng = gpu_util.make_engine(cfg, "bf16", **kw)
+    res = gpu_util.run_step(eng, cfg, params, images, it, progress)
+    eng.close()
+    for k in env:
+        monkeypatch.delenv(k)
+    return res
+
+
+def _same(a, b, tol):
+    assert (a["rgb_pred"] - b["rgb_pred"]).abs().max().item() <= tol
+    for k in ("rgb", "mask", "edge", "all"):
+        assert abs(a["losses"][k] - b["losses"][k]) <= 1e-9 + 1e-6 * abs(b["losses"][k]), k
+    for k, v in b["grads"].items():
+        rel = ((a["grads"][k].double() - v.double()).norm() / (v.double().norm() + 1e-30)).item()
+        assert rel <= tol, (k, rel)
+
+
+def test_one_sweep_multi_chunk_step_matches_two_pass(monkeypatch):
+    """Disk masks, several chunks: forward + backward chunk by chunk in one sweep (static normaliser) against the generic
+    statistics-pass-then-recompute path (MARF_NO_SWEEP=1): same kernels on the same data, only fp32 atomics reorder."""
+    a = _run("mid_mask_c2f", monkeypatch, {}, max_chunk_pixels=1024)
+    b = _run("mid_mask_c2f", monkeypatch, {"MARF_NO_SWEEP": "1"}, max_chunk_pixels=1024)
+    _same(a, b, 1e-4)
+
+
+@pytest.mark.parametrize("env", [{"MARF_NO_FUSED_PROLOGUE": "1"}, {"MARF_EDGE_SPLIT": "1"}])
+def test_merged_launches_match_the_separate_kernels(env, monkeypatch):
+    """The one-launch prologue (pack + expm + class table + zeroing) / the fused Sobel-Gauss-statistics kernel against the
+    separate kernels and memsets they replace."""
+    a = _run("implicit_edges", monkeypatch, {})
+    b = _run("implicit_edges", monkeypatch, env)
+    _same(a, b, 1e-4)
