@@ -342,7 +342,7 @@ def forward(params: PlanarParams, images_rgb: torch.Tensor, cfg: PlanarConfig, p
     uv = warp_grid(xy_b, params.warp)
     rgb = neural_image(uv, params.mlp_w, params.mlp_b, cfg, progress)
     out = dict(rgb_prediction=rgb, rgb_prediction_map=rgb.view(B, h, w, 3).permute(0, 3, 1, 2))
-    out["edge_prediction"] = compute_edges_cv2(out["rgb_prediction_map"])
+    out["edge_prediction"] = compute_edges_cv2(out["rgb_prediction_map"]).to(rgb.device)   # (the reference: .to(opt.device))
     if cfg.use_implicit_mask:
         preds = []
         for im in images_rgb:

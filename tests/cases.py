@@ -26,11 +26,15 @@ STEP_CASES = {
     "mid_mask": dict(MID, use_masks=True),
     "mid_mask_c2f": dict(MID, use_masks=True, barf_c2f=(0.0, 0.4)),
     "mid_nomask_edges": dict(MID, use_masks=False, use_edges=True),
-    # no golden file (oracle-only cases: the oracle itself is pinned by the goldens of the cases above)
-    "wide512_L10": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10),
-    "wide512_c2f": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10, barf_c2f=(0.0, 0.4)),
     "implicit": dict(FULL2, use_masks=True, use_implicit_mask=True),
     "implicit_edges": dict(FULL2, use_masks=True, use_implicit_mask=True, use_edges=True),
+}
+
+
+# cases without a golden file (the oracle itself is pinned by the goldens of STEP_CASES): BASELINE config 5's network
+ORACLE_ONLY_CASES = {
+    "wide512_L10": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10),
+    "wide512_c2f": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10, barf_c2f=(0.0, 0.4)),
 }
 
 
@@ -54,7 +58,7 @@ def make_images(cfg: po.PlanarConfig, seed: int):
 
 def build_case(name):
     """-> (cfg, params, images, it, progress, golden) for a step case."""
-    cfg = po.PlanarConfig(**STEP_CASES[name])
+    cfg = po.PlanarConfig(**(STEP_CASES[name] if name in STEP_CASES else ORACLE_ONLY_CASES[name]))
     implicit = cfg.use_implicit_mask
     seed_w, seed_h, seed_im = (22, 32, 42) if implicit else (21, 31, 41)
     ws, bs = fx.synth_mlp(seed_w, po.layer_shapes(cfg), scale=2.0)

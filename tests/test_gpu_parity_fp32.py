@@ -82,7 +82,7 @@ def _compare(name, res, cfg, params, images, it, progress, g, grad_tol=GRAD_TOL,
     assert res["nonfinite"] == 0.0
 
 
-@pytest.mark.parametrize("name", list(cases.STEP_CASES))
+@pytest.mark.parametrize("name", list(cases.STEP_CASES) + list(cases.ORACLE_ONLY_CASES))
 def test_step_fp32(name):
     import gpu_util
     cfg, params, images, it, progress, g = cases.build_case(name)
