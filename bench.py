@@ -203,6 +203,47 @@ def cpu_reference(wl, steps, warmup, patches=1):
                 ms_per_step=sec * 1e3), n_px
 
 
+def eager_gpu_reference(wl, device, steps=5, warmup=3):
+    """The oracle port (the reference's own eager PyTorch op sequence incl. its per-step OpenCV edge round trip) on the SAME GPU,
+    whole workload: the number a GPU user of the reference gets today.  Informational."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fixtures as fx
+    import planar_oracle as po
+    B = wl["batch"]
+    cfg = po.PlanarConfig(H=wl["H"], W=wl["W"], patch_H=wl["patch_H"], patch_W=wl["patch_W"], batch_size=B,
+                          layers=tuple([None] + wl["layers"]), L_2D=wl["L"], barf_c2f=wl["c2f"], use_masks=wl["masks"],
+                          use_implicit_mask=wl["implicit"], use_edges=wl["edges"])
+    params = po.init_params(cfg, seed=3)
+    rgb, masks = fx.synth_patches(0, B, cfg.h, cfg.w, occluders=True)
+    images = dict(rgb=rgb, masks=masks if wl["masks"] else None, masks_eroded=None, edges=None)
+    if wl["masks"]:
+        images["masks_eroded"] = torch.from_numpy(po.erode5(masks.numpy()))
+    if wl["edges"]:
+        gray = (0.299 * rgb[:, 0:1] + 0.587 * rgb[:, 1:2] + 0.114 * rgb[:, 2:3])
+        images["edges"] = torch.from_numpy(po.sobel_gauss_edges(gray.numpy()))
+    for k in ("mlp_w", "mlp_b", "mask_w", "mask_b"):
+        if getattr(params, k) is not None:
+            setattr(params, k, [t.to(device) for t in getattr(params, k)])
+    params.warp = params.warp.to(device)
+    if params.embed is not None:
+        params.embed = params.embed.to(device)
+    images = {k: (v.to(device) if v is not None else None) for k, v in images.items()}
+    t0 = 0.0
+    for i in range(warmup + steps):
+        if i == warmup:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        with torch.device(device):
+            po.step(params, images, cfg, it=i)
+    torch.cuda.synchronize()
+    sec = (time.perf_counter() - t0) / steps
+    n_px = B * cfg.h * cfg.w
+    return dict(value=n_px / sec, unit="pixel-samples/s", ms_per_step=sec * 1e3, kind="port", device=device,
+                what=f"oracle/planar_oracle.py (the reference's eager PyTorch op sequence, fp32 + autograd, OpenCV edge round trip per step) "
+                     f"on the same GPU, whole workload ({n_px} pixel-samples per step), {steps} timed steps")
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -390,6 +431,11 @@ def run_marf(args):
             base, _ = cpu_reference(wl, steps=3, warmup=1, patches=1)
             line["cpu_baseline"] = dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port",
                                         sample=base["sample"])
+            if wl["batch"] * wl["patch_H"] * wl["patch_W"] <= 1 << 20:      # (eager autograd keeps every activation in fp32)
+                try:
+                    line["eager_gpu_baseline"] = eager_gpu_reference(wl, device)
+                except Exception as ex:                                      # informational leg: never fail the bench line
+                    line["eager_gpu_baseline"] = dict(unavailable=repr(ex)[:200])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
