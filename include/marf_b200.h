@@ -196,6 +196,15 @@ int marf_adam_step(marf_handle* h, const marf_adam_io* io, void* stream);
  * (w = 10**loss_weight, 0 for a disabled term; host array).  sums/out5 are device pointers. */
 int marf_loss_scalars(marf_handle* h, const double* sums, double alpha, const double* weights4, double* out5, void* stream);
 
+/* One-shot all-reduce (sum) over NVLink peer memory for the small exchanges of a data-parallel step (loss sums, gradient
+ * buffer): every rank passes the device pointers of all ranks' inputs and flag arrays (symmetric allocations, e.g.
+ * torch.distributed._symmetric_memory; flag array = 2*world+1 zero-initialised uint32), its rank, and a round number `seq`
+ * that increases by one per call of the group.  dtype 0 = fp32, 1 = fp64.  out == peer_in[rank] (in place) is allowed for
+ * n <= 256.  When the launch has completed no peer reads this rank's input any more.  Replaces the NCCL all-reduce the
+ * host side would otherwise issue (`dist.all_reduce` in marf_b200/planar.py); no handle needed. */
+int marf_peer_allreduce(int device, int dtype, const void* const* peer_in, uint32_t* const* peer_flags, int rank, int world,
+                        void* out, long long n, uint32_t seq, void* stream);
+
 /* diagnostic: run ONE tensor-core kernel (tcgen05) on fp32 device arrays that are rounded to bf16 inside.
  * mode 0: relu(A[rows,K] W[N,K]^T + aux[N]); 1: (A W^T)*(aux[rows,N]>0); 2: plain fp32 out, N=64;
  * 3: out[N,K] = A[rows,N]^T aux[rows,K] (the dW kernel).  Synchronises `stream`.  Used by tests/ only. */

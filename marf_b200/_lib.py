@@ -18,7 +18,7 @@ S_RGB, N_RGB, S_MASK, N_MASK, S_EDGE, N_EDGE, NONFINITE, N_SUMS = 0, 1, 2, 3, 4,
 EXPORTS = [
     "marf_abi_version", "marf_create", "marf_destroy", "marf_last_error", "marf_step", "marf_step_forward",
     "marf_step_backward", "marf_render", "marf_sl3_to_SL3", "marf_warp_corners", "marf_warp_points", "marf_compute_edges",
-    "marf_launch_count", "marf_workspace_bytes", "marf_tc_selftest", "marf_adam_step", "marf_debug_read_bf16", "marf_profile", "marf_profile_read", "marf_loss_scalars",
+    "marf_launch_count", "marf_workspace_bytes", "marf_tc_selftest", "marf_adam_step", "marf_debug_read_bf16", "marf_profile", "marf_profile_read", "marf_loss_scalars", "marf_peer_allreduce",
 ]
 
 _i32, _u32, _i64, _f32, _f64, _vp = C.c_int32, C.c_uint32, C.c_int64, C.c_float, C.c_double, C.c_void_p
@@ -110,6 +110,8 @@ def load():
     lib.marf_profile_read.restype = C.c_int
     lib.marf_loss_scalars.argtypes = [_vp, _vp, C.c_double, C.POINTER(C.c_double), _vp, _vp]
     lib.marf_loss_scalars.restype = C.c_int
+    lib.marf_peer_allreduce.argtypes = [C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.c_int, C.c_int, _vp, C.c_longlong, _u32, _vp]
+    lib.marf_peer_allreduce.restype = C.c_int
     lib.marf_adam_step.argtypes = [_vp, C.POINTER(MarfAdamIO), _vp]
     lib.marf_adam_step.restype = C.c_int
     lib.marf_launch_count.argtypes = [_vp]

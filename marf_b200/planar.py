@@ -196,6 +196,19 @@ class Graph(torch.nn.Module):
             self._grad_slices.append((off, off + p.numel(), tuple(p.shape)))
             off += p.numel()
         self._grad_views = [self._grad_flat[a:b].view(shape) for a, b, shape in self._grad_slices]
+        # data parallel: the step's two small exchanges as one-shot all-reduces over NVLink peer memory (marf_peer_allreduce);
+        # the engine then writes its gradients and loss sums into this rank's symmetric buffer.  NCCL (dist.all_reduce) when
+        # symmetric memory is not available or MARF_NCCL_ALLREDUCE is set.
+        self._peer, self._step_grad_views = None, self._grad_views
+        if self._dp() and world > 1 and not os.environ.get("MARF_NCCL_ALLREDUCE"):
+            try:
+                from .peer import PeerAllReduce
+                self._peer = PeerAllReduce(dev, total)
+                self._step_grad_views = [self._peer.grad_local[a:b].view(shape) for a, b, shape in self._grad_slices]
+                self.engine.sums = self._peer.sums
+            except Exception as ex:            # pylint: disable=broad-except
+                print(f"[marf_b200] peer all-reduce unavailable ({ex!r}); using NCCL", flush=True)
+                self._peer, self._step_grad_views = None, self._grad_views
         e = self.engine
         self._rgb_pred = torch.zeros(e.batch, e.rows * e.w, 3, dtype=torch.float32, device=dev)
         self._mask_pred = torch.zeros(e.batch, e.rows * e.w, 1, dtype=torch.float32, device=dev) \
@@ -232,6 +245,19 @@ class Graph(torch.nn.Module):
         e.bump_data_version()
         return loc
 
+    def _allreduce(self, sums, grads):
+        """The exchange step of data parallelism: loss sums (in place) and / or the flat gradient buffer."""
+        if self._peer is not None:
+            if sums is not None:
+                self._peer.allreduce_sums()
+            if grads:
+                self._peer.allreduce_grads(self._grad_flat)
+        else:
+            if sums is not None:
+                dist.all_reduce(sums)
+            if grads:
+                dist.all_reduce(self._grad_flat)
+
     def loss_coefficients(self):
         """(c_rgb, c_mask, c_edge, alpha): loss.all = c_rgb·rgb + c_mask·mask + c_edge·edge once `render` is
         expanded (model/planar.py:359,371-378) and weighted by 10**loss_weight (:177-184)."""
@@ -255,7 +281,7 @@ class Graph(torch.nn.Module):
         ws, bs = self.neural_image.weights()
         implicit = bool(opt.use_implicit_mask)
         nl = len(ws)
-        gv = self._grad_views
+        gv = self._step_grad_views
         kw = dict(mlp_w=[w.detach() for w in ws], mlp_b=[b.detach() for b in bs], warp=self.warp_param.weight.detach(),
                   rgb=loc.rgb, masks=loc.masks if (opt.use_masks and not implicit) else None,
                   masks_eroded=loc.masks_eroded if (opt.use_masks and not implicit and opt.use_edges) else None,
@@ -276,13 +302,12 @@ class Graph(torch.nn.Module):
         elif not implicit:
             kw["norm_rgb"], kw["norm_edge"] = self._norms
             sums = e.step(**kw)
-            dist.all_reduce(sums)
-            dist.all_reduce(self._grad_flat)
+            self._allreduce(sums, grads=True)
         else:
             sums = e.step_forward(**kw)
-            dist.all_reduce(sums)
+            self._allreduce(sums, grads=False)
             e.step_backward()
-            dist.all_reduce(self._grad_flat)
+            self._allreduce(None, grads=True)
         self._sums = sums
         B = e.batch
         var.rgb_prediction = self._rgb_pred

@@ -50,7 +50,9 @@ def main():
         g.it = 700
         g.neural_image.progress.data.fill_(0.2)
         var = AttrDict(idx=torch.arange(opt.batch_size), images=m.images)
-        g.forward(var, mode="train")
+        for _ in range(3):                      # (consecutive rounds of the exchange: flags / sequence numbers must line up)
+            g.it = 700
+            g.forward(var, mode="train")
         loss_d = [float(x) for x in g.engine.loss_values(g._sums)]
         grad_d = g._grad_flat.clone()
         # the same problem on one rank
@@ -67,7 +69,8 @@ def main():
         ok = gerr <= tol_g and lerr <= tol_l
         e = g.engine
         print(f"[rank {rank}/{world}] {case}: shard(batch={e.batch}, patch_offset={e.patch_offset}, rows={e.rows}, "
-              f"row_offset={e.row_offset}) grad rel-L2 err {gerr:.2e}, loss rel err {lerr:.2e} {'OK' if ok else 'FAIL'}", flush=True)
+              f"row_offset={e.row_offset}) exchange={'peer' if g._peer is not None else 'nccl'} grad rel-L2 err {gerr:.2e}, "
+              f"loss rel err {lerr:.2e} {'OK' if ok else 'FAIL'}", flush=True)
         if not ok:
             failures.append(case)
         g.engine.close()
