@@ -200,7 +200,10 @@ class Graph(torch.nn.Module):
         # the engine then writes its gradients and loss sums into this rank's symmetric buffer.  NCCL (dist.all_reduce) when
         # symmetric memory is not available or MARF_NCCL_ALLREDUCE is set.
         self._peer, self._step_grad_views = None, self._grad_views
-        if self._dp() and world > 1 and not os.environ.get("MARF_NCCL_ALLREDUCE"):
+        # (measured on one 8x B200 box: the one-shot exchange wins at 2 and 4 ranks — 0.935 vs 0.956 ms/step at 2 — and loses at
+        #  8, where every rank reads 8 x 2 MB over NVLink while NCCL reduces inside the switch (NVLS): 1.030 vs 0.990 ms/step)
+        peer_max = int(os.environ.get("MARF_PEER_ALLREDUCE_MAX_WORLD", "4"))
+        if self._dp() and 1 < world <= peer_max and not os.environ.get("MARF_NCCL_ALLREDUCE"):
             try:
                 from .peer import PeerAllReduce
                 self._peer = PeerAllReduce(dev, total)
