@@ -1,6 +1,9 @@
 // precision=bf16: the tensor-core path.  bf16 activations/weights, fp32 accumulation in TMEM (tcgen05.mma),
-// fp32 master weights and gradients.  Per layer: one k_tc_gemm launch forward, one for dX, one k_tc_dw for dW;
-// encodings, the 3-/1-wide output layers, losses and reductions are SIMT kernels.  No fallback to the fp32 path.
+// fp32 master weights and gradients.  A step of the 256-wide networks is 10 launches: prologue (weight pack + homographies +
+// mask class table + zeroing), encoding, k_tc_chain<fwd> (all layers of both MLPs on CTA pairs), loss statistics, edge
+// branch, loss gradients, k_tc_chain<dx>, the dX0 / warp-gradient GEMM, k_tc_dw (every dW / db), tail (mask layer-0
+// gradients + sl(3) adjoint + gradient hand-over).  512-wide networks and MARF_NO_FUSE run the per-layer k_tc_gemm launches
+// with SIMT 3-/1-wide output layers.  No fallback to the fp32 path.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -66,43 +69,6 @@ __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, b
     o[j] = make_uint4(tc::pack_bf16(f[8 * j], f[8 * j + 1]), tc::pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                       tc::pack_bf16(f[8 * j + 4], f[8 * j + 5]), tc::pack_bf16(f[8 * j + 6], f[8 * j + 7]));
   for (int j = 8; j < ld / 8; ++j) o[j] = make_uint4(0u, 0u, 0u, 0u);
-}
-
-// mask-head features (model/planar.py:342-349) in bf16, one block per pixel row
-__global__ void k_mask_features_bf16(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
-                                     int embed_dim, int n_freqs, bf16* __restrict__ F, int ld) {
-  pdl_wait();
-  int t = blockIdx.x;
-  bf16* o = F + (size_t)t * ld;
-  if (t >= rg.count) {
-    for (int j = threadIdx.x; j < ld; j += blockDim.x) o[j] = __float2bfloat16(0.f);
-    return;
-  }
-  int b, r, c;
-  long long i = rg.first + t;
-  decode_px(g, i, b, r, c);
-  long long per = (long long)g.rows * g.w;
-  long long rem = i - (long long)b * per;
-  int k_col = 3 * embed_dim;
-  for (int j = threadIdx.x; j < k_col; j += blockDim.x) {
-    int ch = j / embed_dim, e = j - ch * embed_dim;
-    long long idx = (long long)rgb[((long long)b * 3 + ch) * per + rem];
-    o[j] = __float2bfloat16(embed[idx * embed_dim + e]);
-  }
-  float x, y;
-  grid_xy(g, r, c, x, y);
-  int k_uv = 2 + 4 * n_freqs;
-  for (int j = threadIdx.x; j < k_uv; j += blockDim.x) {
-    float val;
-    if (j < 2) val = j == 0 ? x : y;
-    else {
-      int q = j - 2, fi = q / 4, w4 = q % 4;
-      float a = (float)(1 << fi) * ((w4 & 1) ? y : x);
-      val = (w4 < 2) ? sinf(a) : cosf(a);
-    }
-    o[k_col + j] = __float2bfloat16(val);
-  }
-  for (int j = k_col + k_uv + threadIdx.x; j < ld; j += blockDim.x) o[j] = __float2bfloat16(0.f);
 }
 
 // ---- mask head layer 0 through the colour-class table (model/planar.py:342-349).  trunc(rgb) of a [0,1] image is 0 or 1,
@@ -182,32 +148,11 @@ __global__ void k_mask_table(const float* __restrict__ W0, const float* __restri
   mask_table_block(blockIdx.x, W0, b0, embed, k_in, k_out, edim, k_uv, Wk, ldk);
 }
 
-// Layer-0 gradient of the mask head from the dW tile X = dY0^T [uv | onehot | onehot] ([k_out, 64] fp32):
+// Layer-0 gradient of the mask head from the dW tile X = dY0^T [uv | onehot | onehot] ([k_out, 64] fp32) — computed by the
+// tail launch (k_unpack_table modes 1 / 2):
 //   uv columns          -> dW0[:, 3E : 3E + k_uv]
 //   S[c][j] = X[j][k_uv + c] (per-class column sums of dY0)
 //   dW0[j][ch*E + e] = sum_c S[c][j] * embed[bit_ch(c)][e],   db0[j] = sum_c S[c][j]
-__global__ void k_mask_dw_finalize(const float* __restrict__ X, const float* __restrict__ embed, int edim, int k_out, int k_uv,
-                                   float* __restrict__ gW0, int ldw, float* __restrict__ gb0) {
-  pdl_wait();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ncol = 3 * edim + k_uv;
-  if (i >= k_out * ncol) return;
-  const int j = i / ncol, col = i - j * ncol;
-  const float* x = X + (size_t)j * 64;
-  if (col >= 3 * edim) {
-    gW0[(size_t)j * ldw + col] = x[col - 3 * edim];
-    return;
-  }
-  const int ch = col / edim, e = col - ch * edim;
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float v = x[k_uv + c];
-    if ((c >> ch) & 1) s1 += v; else s0 += v;
-  }
-  gW0[(size_t)j * ldw + col] = s0 * embed[e] + s1 * embed[edim + e];
-  if (col == 0) gb0[j] = s0 + s1;
-}
 
 // W fp32 [rows, cols] -> bf16 [prow, pcol] (zero padded), optionally transposed: out[c][r]
 __global__ void k_pack_bf16(const float* __restrict__ W, int rows, int cols, bf16* __restrict__ out, int prow, int pcol,
@@ -444,8 +389,8 @@ static __global__ void k_pack_table(const __grid_constant__ PackTable t) {
   }
 }
 // The tail of the backward pass in ONE launch: every gradient from its padded fp32 twin to the caller's tensor (mode 0), the
-// mask head's layer-0 weight / bias gradients straight from the class-table scratch (modes 1 / 2: what k_mask_dw_finalize
-// computes, without the round trip through the padded twin), and — row t.n of the grid — the sl(3) adjoint of every owned
+// mask head's layer-0 weight / bias gradients straight from the class-table scratch (modes 1 / 2, without a
+// round trip through the padded twin), and — row t.n of the grid — the sl(3) adjoint of every owned
 // patch plus the zero rows of the patches other ranks own.
 struct UnpackEntry { const float* src; float* dst; int rows, cols, pcol; int mode; const float* embed; int edim, k_uv; };
 struct UnpackTable {
@@ -1011,7 +956,7 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
         for (int t = 0; t < n_tiles_n; ++t) {
           if (l == 0 && B.col_off0 > 0)
             // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to a scratch that
-            // k_mask_dw_finalize turns into dW0 / db0
+            // the tail launch (k_unpack_table modes 1 / 2) turns into dW0 / db0
             add(B.tmDY64[l], B.tmAct64[l], n_tile, m0, L.k_out, 64, t * n_tile, 64, 0, B.dW0x, F.gbp[l]);
           else
             add(B.tmDY64[l], B.tmAct64[l], n_tile, m0, L.k_out, L.k_in, t * n_tile, F.ld_in[l], t == 0, F.gWp[l], F.gbp[l]);
