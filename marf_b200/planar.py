@@ -202,16 +202,20 @@ class Graph(torch.nn.Module):
         self._peer, self._step_grad_views = None, self._grad_views
         # (measured on one 8x B200 box: the one-shot exchange wins at 2 and 4 ranks — 0.935 vs 0.956 ms/step at 2 — and loses at
         #  8, where every rank reads 8 x 2 MB over NVLink while NCCL reduces inside the switch (NVLS): 1.030 vs 0.990 ms/step)
+        #  -> gradients over peer memory up to 4 ranks; the 64-byte loss sums (pure latency) over peer memory at any size)
         peer_max = int(os.environ.get("MARF_PEER_ALLREDUCE_MAX_WORLD", "4"))
-        if self._dp() and 1 < world <= peer_max and not os.environ.get("MARF_NCCL_ALLREDUCE"):
+        self._peer_grads = False
+        if self._dp() and 1 < world <= 8 and not os.environ.get("MARF_NCCL_ALLREDUCE"):
             try:
                 from .peer import PeerAllReduce
                 self._peer = PeerAllReduce(dev, total)
-                self._step_grad_views = [self._peer.grad_local[a:b].view(shape) for a, b, shape in self._grad_slices]
+                self._peer_grads = world <= peer_max
+                if self._peer_grads:
+                    self._step_grad_views = [self._peer.grad_local[a:b].view(shape) for a, b, shape in self._grad_slices]
                 self.engine.sums = self._peer.sums
             except Exception as ex:            # pylint: disable=broad-except
                 print(f"[marf_b200] peer all-reduce unavailable ({ex!r}); using NCCL", flush=True)
-                self._peer, self._step_grad_views = None, self._grad_views
+                self._peer, self._peer_grads, self._step_grad_views = None, False, self._grad_views
         e = self.engine
         self._rgb_pred = torch.zeros(e.batch, e.rows * e.w, 3, dtype=torch.float32, device=dev)
         self._mask_pred = torch.zeros(e.batch, e.rows * e.w, 1, dtype=torch.float32, device=dev) \
@@ -250,15 +254,15 @@ class Graph(torch.nn.Module):
 
     def _allreduce(self, sums, grads):
         """The exchange step of data parallelism: loss sums (in place) and / or the flat gradient buffer."""
-        if self._peer is not None:
-            if sums is not None:
+        if sums is not None:
+            if self._peer is not None:
                 self._peer.allreduce_sums()
-            if grads:
-                self._peer.allreduce_grads(self._grad_flat)
-        else:
-            if sums is not None:
+            else:
                 dist.all_reduce(sums)
-            if grads:
+        if grads:
+            if self._peer_grads:
+                self._peer.allreduce_grads(self._grad_flat)
+            else:
                 dist.all_reduce(self._grad_flat)
 
     def loss_coefficients(self):

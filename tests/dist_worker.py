@@ -69,7 +69,7 @@ def main():
         ok = gerr <= tol_g and lerr <= tol_l
         e = g.engine
         print(f"[rank {rank}/{world}] {case}: shard(batch={e.batch}, patch_offset={e.patch_offset}, rows={e.rows}, "
-              f"row_offset={e.row_offset}) exchange={'peer' if g._peer is not None else 'nccl'} grad rel-L2 err {gerr:.2e}, "
+              f"row_offset={e.row_offset}) exchange={'peer' if g._peer_grads else ('peer-sums+nccl' if g._peer is not None else 'nccl')} grad rel-L2 err {gerr:.2e}, "
               f"loss rel err {lerr:.2e} {'OK' if ok else 'FAIL'}", flush=True)
         if not ok:
             failures.append(case)
