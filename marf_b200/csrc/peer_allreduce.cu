@@ -7,7 +7,7 @@
 //   3. publishes "I have finished reading" and waits for the same from all peers, so that when the launch completes nobody is
 //      still reading this rank's input and the next step may overwrite it.
 // NCCL's ring / tree needs ~20-40 us for these sizes on 8 GPUs; this is one NVLink round trip plus 2 MB x world of peer reads.
-// Spins are bounded: a missing peer traps (CUDA error at the next call) instead of hanging the GPU.
+// Spins are bounded (minutes): a missing peer traps (CUDA error at the next call) instead of hanging the GPU for good.
 #include "common.cuh"
 
 namespace marf {
@@ -34,9 +34,10 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void wait_all(const uint32_t* my_flags, int world, uint32_t seq) {
   if ((int)threadIdx.x < world) {
     uint32_t spins = 0;
+    // (bounded, but generously: ranks of a training job drift by seconds around checkpoints / visualisation; ~1-2 minutes)
     while ((int32_t)(ld_acquire_sys(my_flags + threadIdx.x) - seq) < 0) {
-      __nanosleep(32);
-      if (++spins > (1u << 25)) __trap();
+      __nanosleep(spins < 1024 ? 32 : 256);
+      if (++spins > (1u << 28)) __trap();
     }
   }
   __syncthreads();

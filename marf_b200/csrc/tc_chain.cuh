@@ -408,8 +408,12 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
           if (valid) {
             named_bar_sync(3 + grp, 128);                  // all 128 rows of both slabs are in SMEM
             if (gleader && !(jobs.dbg & 1)) {
-              tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, kEvictFirst);
-              tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, kEvictFirst);
+              // forward activations are next read by the dW pass, a whole backward pass later: evict first.  The dY of the dX
+              // chain are read by the dX0 GEMM and the dW launch right after this kernel: normal priority, so that what the L2
+              // still holds of them at the end of the kernel is served from there.
+              const uint64_t pol = MODE == CH_FWD ? kEvictFirst : kEvictNormal;
+              tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, pol);
+              tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, pol);
               bulk_commit();
             }
           }
