@@ -447,9 +447,9 @@ static int edge_pass(marf_handle* h, const marf_step_io* io, cudaStream_t st) {
   e.edge_pred = ep; e.edge_label = io->edges; e.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
   e.masks_eroded = io->masks_eroded;
   e.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
-  if (c.rows >= 8 && h->w >= 8 && c.batch <= 65535 && !getenv("MARF_EDGE_SPLIT")) {
+  if (c.rows >= 8 && h->w >= 8 && c.batch * 3 <= 65535 && !getenv("MARF_EDGE_SPLIT")) {
     // Sobel -> Gauss -> statistics in one launch (the reflected window positions stay inside a block's window for images >= 8x8)
-    const dim3 ef((unsigned)((h->w + kEfW - 1) / kEfW), (unsigned)((c.rows + kEfH - 1) / kEfH), (unsigned)c.batch);
+    const dim3 ef((unsigned)((h->w + kEfW - 1) / kEfW), (unsigned)((c.rows + kEfH - 1) / kEfH), (unsigned)(c.batch * 3));
     launch_k(k_edge_fused, ef, 256, 0, st, pred, c.rows, h->w, e, ep, io->loss_sums);
     LAUNCH_CHECK(h);
     return MARF_OK;

@@ -758,8 +758,8 @@ static __global__ void k_sobel_mag(const float* __restrict__ img, int n, int ch,
 }
 
 // Sobel magnitude -> 5x5 Gaussian -> edge statistics of one step in ONE launch (replaces k_sobel_mag + k_gauss5 + k_edge_stats
-// on the training path; same fp64 operation order, so the results are bit-identical).  Block = 32x8 output pixels of one
-// image; per channel: the 38x14 input window (REFLECT_101 resolved while loading) and the 36x12 magnitude window live in SMEM.
+// on the training path; same fp64 operation order per pixel, so edge_pred is bit-identical).  Block = 32x8 output pixels of one
+// channel of one image: the 38x14 input window (REFLECT_101 resolved while loading) and the 36x12 magnitude window live in SMEM.
 // A magnitude outside the image is the magnitude AT the reflected position, as OpenCV's two-pass evaluation gives.
 constexpr int kEfW = 32, kEfH = 8;
 static __global__ void __launch_bounds__(256) k_edge_fused(const float* __restrict__ pred /* [batch, rows*w, 3] */, int rows, int w, EdgeArgs a,
@@ -769,7 +769,8 @@ static __global__ void __launch_bounds__(256) k_edge_fused(const float* __restri
   __shared__ double s_in[kEfH + 6][kEfW + 6];
   __shared__ double s_mag[kEfH + 4][kEfW + 4];
   __shared__ double red[32];
-  const int b = blockIdx.z, x0 = blockIdx.x * kEfW, y0 = blockIdx.y * kEfH;
+  const int b = blockIdx.z / 3, c = blockIdx.z - 3 * b;      // one (image, channel) per block: three times the parallelism
+  const int x0 = blockIdx.x * kEfW, y0 = blockIdx.y * kEfH;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int x = x0 + tx, y = y0 + ty;
   const bool inside = x < w && y < rows;
@@ -783,8 +784,7 @@ static __global__ void __launch_bounds__(256) k_edge_fused(const float* __restri
   double s_acc = 0.0;
   const double sk[3] = {1, 2, 1}, dk[3] = {-1, 0, 1};
   const double g5[5] = {1.0 / 16, 4.0 / 16, 6.0 / 16, 4.0 / 16, 1.0 / 16};
-  for (int c = 0; c < 3; ++c) {
-    __syncthreads();
+  {
     for (int i = threadIdx.x; i < (kEfH + 6) * (kEfW + 6); i += 256) {
       const int iy = i / (kEfW + 6), ix = i - iy * (kEfW + 6);
       const int yy = reflect101(y0 - 3 + iy, rows), xx = reflect101(x0 - 3 + ix, w);
@@ -825,7 +825,7 @@ static __global__ void __launch_bounds__(256) k_edge_fused(const float* __restri
     }
   }
   block_sum_atomic(s_acc, &sums[MARF_S_EDGE], red);
-  block_sum_atomic(inside ? 3.0 * m : 0.0, &sums[MARF_N_EDGE], red);
+  block_sum_atomic(inside ? m : 0.0, &sums[MARF_N_EDGE], red);        // (the three channel blocks of a pixel add m each: 3 m)
 }
 
 static __global__ void k_gauss5(const double* __restrict__ mag, int planes, int rows, int w, double* __restrict__ out) {
