@@ -446,6 +446,48 @@ class Model(torch.nn.Module):
     def _is_main():
         return not _dist_on() or dist.get_rank() == 0
 
+    # ------------------------------------------------------------------ checkpoints
+    # The reference's config carries `load` / `resume` (options/planar.yaml:31,88) but no code behind them; here:
+    #   --resume        restart from <output_path>/model.ckpt if it exists (written every freq.ckpt iterations and at the end)
+    #   --load=<file>   initialise the networks and warps from a checkpoint, iteration counter reset
+    def checkpoint_path(self):
+        return os.path.join(self.opt.output_path, "model.ckpt")
+
+    def save_checkpoint(self, path=None):
+        """Networks, warps, optimizer moments and iteration counters; rank 0 writes (the replicas are identical)."""
+        if not self._is_main():
+            return None
+        path = path or self.checkpoint_path()
+        ck = dict(version=1, it=self.it, graph_it=self.graph.it, graph=self.graph.state_dict())
+        if self.fused_tail is not None:
+            ft = self.fused_tail
+            ck["fused_adam"] = dict(step=ft.step_count, exp_avg=[t.clone() for t in ft.exp_avg], exp_avg_sq=[t.clone() for t in ft.exp_avg_sq])
+        elif self.optim is not None:
+            ck["optim"] = self.optim.state_dict()
+        tmp = path + ".tmp"
+        torch.save(ck, tmp)
+        os.replace(tmp, path)                      # (never leaves a half-written checkpoint behind)
+        return path
+
+    def load_checkpoint(self, path, resume=True):
+        """resume=True: also optimizer state and iteration counters (continue the run); False: parameters only."""
+        ck = torch.load(path, map_location=self.opt.device, weights_only=False)
+        self.graph.load_state_dict(ck["graph"])
+        if not resume:
+            return 0
+        self.it, self.graph.it = int(ck["it"]), int(ck["graph_it"])
+        self.graph.neural_image.progress.data.fill_(self.it / self.opt.max_iter)
+        if self.fused_tail is not None and "fused_adam" in ck:
+            ft, st = self.fused_tail, ck["fused_adam"]
+            ft.step_count = int(st["step"])
+            for dst, src in zip(ft.exp_avg, st["exp_avg"]):
+                dst.copy_(src)
+            for dst, src in zip(ft.exp_avg_sq, st["exp_avg_sq"]):
+                dst.copy_(src)
+        elif self.optim is not None and "optim" in ck:
+            self.optim.load_state_dict(ck["optim"])
+        return self.it
+
     def train(self, mode=True):  # pylint: disable=arguments-differ,unused-argument
         """model/planar.py:136-170."""
         import tqdm
@@ -456,14 +498,26 @@ class Model(torch.nn.Module):
         var.images = self.images
         var = inputs.move_to_device(var, self.opt.device)
         self.images = var.images
-        loader = tqdm.trange(self.opt.max_iter, desc="Training", leave=False, disable=not self._is_main())
+        start = 0
+        if self.opt.get("load"):
+            self.load_checkpoint(self.opt.load, resume=False)
+            print(f"initialised from {self.opt.load}")
+        if self.opt.get("resume") and os.path.exists(self.checkpoint_path()):
+            start = self.load_checkpoint(self.checkpoint_path(), resume=True)
+            print(f"resumed from {self.checkpoint_path()} at iteration {start}")
+        freq_ckpt = int(self.opt.freq.get("ckpt", 0) or 0)
+        loader = tqdm.trange(start, self.opt.max_iter, desc="Training", leave=False, disable=not self._is_main())
         with torch.no_grad():
             var = self.graph.forward(var)
-        self.visualize(var, step=0)
+        if start == 0:
+            self.visualize(var, step=0)
         for _ in loader:
             self.train_iteration(var, loader)
             if self.opt.warp.fix_first:
                 self.graph.warp_param.weight.data[0] = 0
+            if freq_ckpt and self.it % freq_ckpt == 0:
+                self.save_checkpoint()
+        self.save_checkpoint()
         if self._is_main() and os.system("command -v ffmpeg > /dev/null 2>&1") == 0:
             os.system(f"ffmpeg -y -framerate 30 -i {self.vis_path}/%d.png -pix_fmt yuv420p {self.video_fname}")
         if self.tb:

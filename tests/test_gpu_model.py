@@ -99,3 +99,46 @@ def test_synthetic_scene_and_corner_metric(tmp_path):
     # identical warps -> zero corner error
     m.graph.warp_param.weight.data.copy_(m.images.gt_warp)
     assert float(m.corner_error_px(m.images.gt_warp)) < 1e-4
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_checkpoint_resume_continues_the_run(tmp_path, fused):
+    """save_checkpoint / load_checkpoint: 4 iterations, checkpoint, 4 more == restore in a fresh Model, 4 more.
+    Parameters, Adam moments and the iteration / schedule counters travel; the fp32 step's atomics reorder sums, hence a
+    tolerance instead of bit equality."""
+    from marf_b200.attrdict import AttrDict
+    from marf_b200 import planar
+
+    def make():
+        opt = _opt(tmp_path, H=72, W=96, patch_H=36, patch_W=48, batch_size=3, max_iter=200, use_masks=True, use_edges=False,
+                   barf_c2f=[0.0, 0.4], fused_optimizer=fused, synthetic=dict(enabled=True, seed=2, occluders=True))
+        torch.manual_seed(3)
+        m = planar.Model(opt)
+        m.load_dataset()
+        m.build_networks()
+        m.setup_optimizer()
+        m.setup_visualizer()
+        m.timer = AttrDict(start=0.0, it_mean=None)
+        return m, AttrDict(idx=torch.arange(3), images=m.images)
+
+    def run(m, var, n):
+        for _ in range(n):
+            m.train_iteration(var, _Loader())
+            if m.opt.warp.fix_first:
+                m.graph.warp_param.weight.data[0] = 0
+
+    a, var = make()
+    run(a, var, 4)
+    path = a.save_checkpoint()
+    run(a, var, 4)
+    b, var_b = make()
+    assert b.load_checkpoint(path, resume=True) == 4 and b.graph.it == a.graph.it - 4
+    run(b, var_b, 4)
+    assert b.it == a.it == 8
+    for (k, pa), (_, pb) in zip(a.graph.state_dict().items(), b.graph.state_dict().items()):
+        err = (pa.double() - pb.double()).abs().max().item()
+        assert err <= 1e-5 * (pa.double().abs().max().item() + 1e-6) + 1e-7, (k, err)
+    # parameters only
+    c, _ = make()
+    assert c.load_checkpoint(path, resume=False) == 0 and c.it == 0
+    torch.testing.assert_close(c.graph.warp_param.weight, torch.load(path, weights_only=False)["graph"]["warp_param.weight"].to("cuda:0"))
