@@ -16,7 +16,9 @@
  *   - plain C types only; every pointer in the *_io structs is a DEVICE pointer owned by the
  *     caller (they are torch.Tensor.data_ptr()s in the Python host) unless marked "host";
  *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no entry
- *     point synchronises the device except marf_create / marf_destroy;
+ *     point synchronises the device or the stream except marf_create / marf_destroy and the three
+ *     diagnostics that say so (marf_tc_selftest, marf_debug_read_bf16, marf_profile_read), so every
+ *     step / render / optimizer call can be captured into a CUDA graph;
  *   - every entry point returns 0 on success, else a marf_status / cudaError_t value;
  *     marf_last_error() returns a human-readable message for the last failure on that handle;
  *   - nothing throws across the ABI; asynchronous CUDA faults surface at the next call;
@@ -32,7 +34,7 @@
 extern "C" {
 #endif
 
-#define MARF_ABI_VERSION 1
+#define MARF_ABI_VERSION 2
 #define MARF_MAX_LAYERS 12
 
 typedef struct marf_handle marf_handle;
@@ -89,6 +91,11 @@ typedef struct marf_config {
   int32_t edge_label_channels;/* channels of images.edges (1: computed from the grey image) */
   /* workspace policy */
   int64_t max_chunk_pixels;   /* 0 = library default; pixel-samples processed per pass */
+  /* (ABI 2) rows of embedding_view (opt.N_vocab, model/planar.py:327): colour indices trunc(rgb) outside
+   * [0, mask_n_vocab) raise IndexError in the reference; here they are clamped and COUNTED in
+   * loss_sums[MARF_BAD_INDEX] (bf16 mode: the class table serves indices {0,1} only, anything else counts). 0 = 1500. */
+  int32_t mask_n_vocab;
+  int32_t reserved0;
 } marf_config;
 
 /* Per-step inputs/outputs.  Shapes use the LOCAL shard: n = batch*rows*w pixel-samples. */
@@ -131,7 +138,7 @@ typedef struct marf_step_io {
  *   edge = S_EDGE / N_EDGE ) */
 enum marf_sum_slot {
   MARF_S_RGB = 0, MARF_N_RGB = 1, MARF_S_MASK = 2, MARF_N_MASK = 3,
-  MARF_S_EDGE = 4, MARF_N_EDGE = 5, MARF_NONFINITE = 6, MARF_N_SUMS = 8
+  MARF_S_EDGE = 4, MARF_N_EDGE = 5, MARF_NONFINITE = 6, MARF_BAD_INDEX = 7, MARF_N_SUMS = 8
 };
 
 /* Forward-only render of the neural image (Model.predict_entire_image, model/planar.py:211-217,
@@ -160,6 +167,12 @@ int marf_step_forward(marf_handle* h, const marf_step_io* io, void* stream);
 int marf_step_backward(marf_handle* h, const marf_step_io* io, void* stream);
 
 int marf_render(marf_handle* h, const marf_render_io* io, void* stream);
+
+/* NeuralImageFunction.forward(coord_2d) for caller-supplied coordinates (model/planar.py:429-449): xy [n,2] are the
+ * ALREADY WARPED normalised coordinates (what Graph.forward passes at model/planar.py:334); positional encoding with the
+ * c2f weights of `progress`, the MLP and the sigmoid run on device; rgb [n,3].  Any n >= 1 (processed in passes). */
+int marf_forward_points(marf_handle* h, const float* const* mlp_w, const float* const* mlp_b, const float* xy, int64_t n,
+                        float progress, float* rgb, void* stream);
 
 /* geometry helpers on device (warp.py:83-108): H = expm(A(h)) and the warped crop corners. */
 int marf_sl3_to_SL3(marf_handle* h, const float* warp, int32_t n, float* out9, void* stream);

@@ -9,16 +9,17 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libmarf_b200.so")
 
-MARF_ABI_VERSION = 1
+MARF_ABI_VERSION = 2
 MARF_MAX_LAYERS = 12
 MASK_NONE, MASK_DISK, MASK_IMPLICIT = 0, 1, 2
 FP32, BF16 = 0, 1
-S_RGB, N_RGB, S_MASK, N_MASK, S_EDGE, N_EDGE, NONFINITE, N_SUMS = 0, 1, 2, 3, 4, 5, 6, 8
+S_RGB, N_RGB, S_MASK, N_MASK, S_EDGE, N_EDGE, NONFINITE, BAD_INDEX, N_SUMS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 EXPORTS = [
     "marf_abi_version", "marf_create", "marf_destroy", "marf_last_error", "marf_step", "marf_step_forward",
     "marf_step_backward", "marf_render", "marf_sl3_to_SL3", "marf_warp_corners", "marf_warp_points", "marf_compute_edges",
     "marf_launch_count", "marf_workspace_bytes", "marf_tc_selftest", "marf_adam_step", "marf_debug_read_bf16", "marf_profile", "marf_profile_read", "marf_loss_scalars", "marf_peer_allreduce",
+    "marf_forward_points",
 ]
 
 _i32, _u32, _i64, _f32, _f64, _vp = C.c_int32, C.c_uint32, C.c_int64, C.c_float, C.c_double, C.c_void_p
@@ -35,6 +36,7 @@ class MarfConfig(C.Structure):
         ("mask_uv_freqs", _i32), ("mask_embed_dim", _i32),
         ("use_edges", _i32), ("edge_label_channels", _i32),
         ("max_chunk_pixels", _i64),
+        ("mask_n_vocab", _i32), ("reserved0", _i32),
     ]
 
 
@@ -92,6 +94,8 @@ def load():
         fn.restype = C.c_int
     lib.marf_render.argtypes = [_vp, C.POINTER(MarfRenderIO), _vp]
     lib.marf_render.restype = C.c_int
+    lib.marf_forward_points.argtypes = [_vp, C.POINTER(_vp), C.POINTER(_vp), _vp, _i64, _f32, _vp, _vp]
+    lib.marf_forward_points.restype = C.c_int
     lib.marf_sl3_to_SL3.argtypes = [_vp, _vp, _i32, _vp, _vp]
     lib.marf_sl3_to_SL3.restype = C.c_int
     lib.marf_warp_corners.argtypes = [_vp, _vp, _i32, _vp, _vp]

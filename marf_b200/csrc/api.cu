@@ -221,7 +221,9 @@ extern "C" int marf_create(const marf_config* cfg, marf_handle** out) {
   h->dYb = (float*)ws_alloc(h, f32 ? (size_t)h->chunk * max_ld * sizeof(float) : 16);
   h->coef = (LossCoef*)ws_alloc(h, sizeof(LossCoef));
   h->sums_static = (double*)ws_alloc(h, 4 * sizeof(double));
-  bool ok = h->Hm && h->G && h->dYa && h->dYb && h->coef && h->sums_static;
+  h->bad_index = (double*)ws_alloc(h, sizeof(double));
+  if (h->cfg.mask_n_vocab <= 0) h->cfg.mask_n_vocab = 1500;        // options/planar.yaml N_vocab
+  bool ok = h->Hm && h->G && h->dYa && h->dYb && h->coef && h->sums_static && h->bad_index;
   if (c.skip_mask) {
     h->dX0acc = (float*)ws_alloc(h, (size_t)h->chunk * h->img.ld_in[0] * sizeof(float));
     h->dXscratch = (float*)ws_alloc(h, (size_t)h->chunk * max_ld * sizeof(float));
@@ -396,6 +398,7 @@ static int refresh_data(marf_handle* h, const marf_step_io* io, cudaStream_t st)
   h->data_version_seen = io->data_version;
   h->feats_valid = false;
   CUDA_TRY(h, cudaMemsetAsync(h->sums_static, 0, 4 * sizeof(double), st));
+  CUDA_TRY(h, cudaMemsetAsync(h->bad_index, 0, sizeof(double), st));
   if (h->cfg.mask_mode == MARF_MASK_DISK) {
     launch_k(k_sum_f32, 296, 256, 0, st, io->masks, h->n_local, 3.0, h->sums_static + 0);
     LAUNCH_CHECK(h);
@@ -415,8 +418,8 @@ static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
     if (!(h->feats_valid && h->n_chunks == 1)) {
-      launch_k(k_mask_features, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_uv_freqs,
-                                                 h->msk.act[0], h->msk.ld_in[0]);
+      launch_k(k_mask_features, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_n_vocab,
+               h->cfg.mask_uv_freqs, h->msk.act[0], h->msk.ld_in[0], h->bad_index);
       LAUNCH_CHECK(h);
       h->feats_valid = h->n_chunks == 1;
     }
@@ -432,6 +435,7 @@ static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
+    a.bad_index = h->cfg.mask_mode == MARF_MASK_IMPLICIT ? h->bad_index : nullptr;
     launch_k(k_loss_stats, std::min((rg.padded + 255) / 256, 592), 256, 0, st, h->geo, rg, a, io->loss_sums);
     LAUNCH_CHECK(h);
   }
@@ -473,7 +477,7 @@ static int backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t s
   ga.l.logits = h->img.act[h->img.n]; ga.l.ld = h->img.ld_out[h->img.n - 1];
   ga.l.mlogits = implicit ? h->msk.act[h->msk.n] : nullptr;
   ga.l.mld = implicit ? h->msk.ld_out[h->msk.n - 1] : 0;
-  ga.l.rgb = io->rgb; ga.l.masks = io->masks; ga.l.rgb_pred = nullptr; ga.l.mask_pred = nullptr;
+  ga.l.rgb = io->rgb; ga.l.masks = io->masks; ga.l.rgb_pred = nullptr; ga.l.mask_pred = nullptr; ga.l.bad_index = nullptr;
   ga.c_rgb = io->c_rgb; ga.c_mask = io->c_mask; ga.c_edge = io->c_edge;
   ga.edge_pred = (implicit && c.use_edges) ? (io->edge_pred ? io->edge_pred : h->edge_pred) : nullptr;
   ga.edge_label = io->edges; ga.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;
@@ -650,6 +654,31 @@ extern "C" int marf_render(marf_handle* h, const marf_render_io* io, void* strea
   return MARF_OK;
 }
 
+// NeuralImageFunction.forward(coord_2d) for explicit coordinates (model/planar.py:429-449): fp32 arithmetic in both precision
+// modes (like marf_render: the forward-only path is the <=1e-3 output-parity path)
+extern "C" int marf_forward_points(marf_handle* h, const float* const* mlp_w, const float* const* mlp_b, const float* xy, int64_t n,
+                                   float progress, float* rgb, void* stream) {
+  if (!h) return MARF_ERR_INVALID;
+  if (!mlp_w || !mlp_b || !xy || !rgb || n <= 0) return fail(h, MARF_ERR_INVALID, "bad forward_points args");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+  set_schedule(h, progress);
+  int rc = pack_chain(h, st, h->img, mlp_w, mlp_b);
+  if (rc) return rc;
+  for (int64_t first = 0; first < n; first += h->render_rows) {
+    const int count = (int)std::min<int64_t>(h->render_rows, n - first);
+    const int padded = (int)round_up(count, 128);
+    launch_k(k_encode_points, (padded + 127) / 128, 128, 0, st, h->geo, xy + 2 * first, count, padded, h->img.act[0], h->img.ld_in[0]);
+    LAUNCH_CHECK(h);
+    rc = chain_forward(h, st, h->img, padded);
+    if (rc) return rc;
+    launch_k(k_sigmoid_out, (count + 255) / 256, 256, 0, st, count, h->img.act[h->img.n], h->img.ld_out[h->img.n - 1], rgb + first * 3);
+    LAUNCH_CHECK(h);
+  }
+  h->acts_valid = false;
+  return MARF_OK;
+}
+
 extern "C" int marf_sl3_to_SL3(marf_handle* h, const float* warp, int32_t n, float* out9, void* stream) {
   if (!h) return MARF_ERR_INVALID;
   if (!warp || !out9 || n <= 0) return fail(h, MARF_ERR_INVALID, "bad sl3 args");
@@ -770,9 +799,9 @@ extern "C" int marf_compute_edges(marf_handle* h, const float* images, int32_t n
   if (!images || !out || n <= 0 || c <= 0 || rows <= 0 || w <= 0) return fail(h, MARF_ERR_INVALID, "bad edge args");
   cudaStream_t st = (cudaStream_t)stream;
   long long tot = (long long)n * c * rows * w;
+  if ((long long)n * c > 65535) return fail(h, MARF_ERR_INVALID, "marf_compute_edges: more than 65535 planes");
   double* mag = nullptr;
   CUDA_TRY(h, cudaMallocAsync((void**)&mag, tot * sizeof(double), st));
-  if ((long long)n * c > 65535) return fail(h, MARF_ERR_INVALID, "marf_compute_edges: more than 65535 planes");
   const dim3 eg((unsigned)((rows * w + 255) / 256), (unsigned)(n * c));
   launch_k(k_sobel_mag, eg, 256, 0, st, images, n, c, rows, w, 0, mag);
   LAUNCH_CHECK(h);

@@ -78,7 +78,7 @@ __global__ void k_encode_bf16(Geo g, PxRange rg, const float* __restrict__ Hm, b
 // multiply the hi and lo bf16 halves of the class table T that k_mask_table writes into the packed layer-0 weights, so
 // the colour part needs no epilogue work, and in the dW GEMM the first one-hot group yields the per-class column sums.
 __global__ void k_mask_uv_cls(Geo g, PxRange rg, const float* __restrict__ rgb, int n_freqs, bf16* __restrict__ UV,
-                              int* __restrict__ bad) {
+                              double* __restrict__ bad) {
   pdl_wait();
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= rg.padded) return;
@@ -96,7 +96,7 @@ __global__ void k_mask_uv_cls(Geo g, PxRange rg, const float* __restrict__ rgb, 
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch) {
       long long idx = (long long)rgb[((long long)b * 3 + ch) * per + rem];
-      if (idx < 0 || idx > 1) atomicOr(bad, 1);
+      if (idx < 0 || idx > 1) atomicAdd(bad, 1.0);      // counted, reported through loss_sums[MARF_BAD_INDEX] (no host sync)
       cl |= (unsigned char)((idx & 1) << ch);
     }
     float x, y;
@@ -472,7 +472,6 @@ struct BfChain {
   int col_off0 = 0;                       // class-table mode: layer 0 uses columns [col_off0, col_off0 + k_in) of W0
   float* dW0x = nullptr;                  // [256, 64] fp32: dY0^T [uv | onehot | onehot] (class-table mode)
   float* zero_bias = nullptr;             // [256] zeros: the class table carries b0
-  int* bad = nullptr;                     // device flag: a colour index outside {0,1} was seen
 };
 
 struct Bf16State {
@@ -507,8 +506,7 @@ static int build_bf_chain(marf_handle* h, Bf16State* S, BfChain& B, Chain& F, bo
   if (class_cols > 0) {
     B.dW0x = (float*)ws_alloc(h, 256 * 64 * sizeof(float));
     B.zero_bias = (float*)ws_alloc(h, 256 * sizeof(float));
-    B.bad = (int*)ws_alloc(h, sizeof(int));
-    if (!B.dW0x || !B.zero_bias || !B.bad) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (class table)");
+    if (!B.dW0x || !B.zero_bias) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (class table)");
     if (F.k_out[0] != 256 || F.k_in[0] - class_cols + 16 > 64)
       return fail(h, MARF_ERR_UNSUPPORTED, "bf16 mask head: layer 0 must be 256 wide with at most 48 positional inputs");
   }
@@ -1264,15 +1262,10 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
   BF_LAUNCH(h);
   if (implicit) {
     if (!(h->feats_valid && h->n_chunks == 1)) {
-      launch_k(k_mask_uv_cls, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, io->rgb, c.mask_uv_freqs, S->msk.act[0], S->msk.bad);
+      // the class table needs trunc(rgb) in {0,1} (true for [0,1] images); every chunk is checked on device and the count
+      // of offending indices reaches the host with the loss sums (MARF_BAD_INDEX) — no synchronisation inside the step
+      launch_k(k_mask_uv_cls, (rg.padded + 127) / 128, 128, 0, st, h->geo, rg, io->rgb, c.mask_uv_freqs, S->msk.act[0], h->bad_index);
       BF_LAUNCH(h);
-      if (h->n_chunks == 1) {
-        // once per data version: the class table needs trunc(rgb) in {0,1} (true for [0,1] images; checked, not assumed)
-        int bad = 0;
-        BF_TRY(h, cudaMemcpyAsync(&bad, S->msk.bad, sizeof(int), cudaMemcpyDeviceToHost, st));
-        BF_TRY(h, cudaStreamSynchronize(st));
-        if (bad) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 mask head: colour indices outside {0,1} (images must lie in [0,2))");
-      }
       h->feats_valid = h->n_chunks == 1;
     }
     if (!S->table_done) {                         // (the fused prologue of a single-call step has already written it)
@@ -1310,6 +1303,7 @@ static int bf_forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t
     a.rgb = io->rgb; a.masks = io->masks;
     a.rgb_pred = io->rgb_pred ? io->rgb_pred : h->pred_rgb;
     a.mask_pred = io->mask_pred ? io->mask_pred : h->pred_mask;
+    a.bad_index = implicit ? h->bad_index : nullptr;
     launch_k(k_loss_stats, std::min((rg.padded + 255) / 256, 592), 256, 0, st, h->geo, rg, a, io->loss_sums);
     BF_LAUNCH(h);
   }
@@ -1326,7 +1320,7 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   ga.l.mask_mode = c.mask_mode;
   ga.l.logits = S->img.logits; ga.l.ld = 4;
   ga.l.mlogits = implicit ? S->msk.logits : nullptr; ga.l.mld = 4;
-  ga.l.rgb = io->rgb; ga.l.masks = io->masks; ga.l.rgb_pred = nullptr; ga.l.mask_pred = nullptr;
+  ga.l.rgb = io->rgb; ga.l.masks = io->masks; ga.l.rgb_pred = nullptr; ga.l.mask_pred = nullptr; ga.l.bad_index = nullptr;
   ga.c_rgb = io->c_rgb; ga.c_mask = io->c_mask; ga.c_edge = io->c_edge;
   ga.edge_pred = (implicit && c.use_edges) ? (io->edge_pred ? io->edge_pred : h->edge_pred) : nullptr;
   ga.edge_label = io->edges; ga.label_channels = c.edge_label_channels > 0 ? c.edge_label_channels : 1;

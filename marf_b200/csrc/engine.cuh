@@ -44,6 +44,7 @@ struct marf_handle {
   double* edge_pred = nullptr;
   double* sums_static = nullptr;  // [2]: 3*sum(masks), 3*sum(masks_eroded) of the local shard
   marf::LossCoef* coef = nullptr;
+  double* bad_index = nullptr;    // sticky per data version: colour indices outside the embedding table (-> loss_sums[MARF_BAD_INDEX])
   int64_t data_version_seen = INT64_MIN;
   bool feats_valid = false;    // mask-head input features cached in msk.act[0] (single chunk only)
   bool acts_valid = false;     // forward activations of the (single) chunk are resident for backward

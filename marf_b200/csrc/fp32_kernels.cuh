@@ -214,6 +214,33 @@ static __global__ void k_encode(Geo g, PxRange rg, const float* __restrict__ Hm 
   for (int j = g.d_in; j < ld; ++j) o[j] = 0.0f;
 }
 
+// the same for caller-supplied (already warped) coordinates: NeuralImageFunction.forward(coord_2d), model/planar.py:429-436
+static __global__ void k_encode_points(Geo g, const float* __restrict__ xy, int count, int padded, float* __restrict__ X0, int ld) {
+  pdl_wait();
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= padded) return;
+  float* o = X0 + (size_t)t * ld;
+  if (t >= count) {
+    for (int j = 0; j < ld; ++j) o[j] = 0.0f;
+    return;
+  }
+  const float u = xy[2 * (size_t)t], v = xy[2 * (size_t)t + 1];
+  o[0] = u;
+  o[1] = v;
+  const int L = g.L;
+  for (int k = 0; k < L; ++k) {
+    float su, cu, sv, cv;
+    sincosf(u * g.band_f[k], &su, &cu);
+    sincosf(v * g.band_f[k], &sv, &cv);
+    float wk = g.band_w[k];
+    o[2 + k] = su * wk;
+    o[2 + L + k] = cu * wk;
+    o[2 + 2 * L + k] = sv * wk;
+    o[2 + 3 * L + k] = cv * wk;
+  }
+  for (int j = g.d_in; j < ld; ++j) o[j] = 0.0f;
+}
+
 // backward of the prologue: dX0 [n,ld] -> per-patch G = sum_p dq (x) [x,y,1]  (SURVEY.md §8 a-4,a-5)
 static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restrict__ Hm, const float* __restrict__ dX0,
                                   int ld, double* __restrict__ G /* [batch,9] local patches */) {
@@ -290,7 +317,7 @@ static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restr
 // one block of 128 threads per pixel-sample row; iteration-invariant (cached by the engine when possible).
 // ============================================================================================
 static __global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
-                                int embed_dim, int n_freqs, float* __restrict__ F, int ld) {
+                                int embed_dim, int n_vocab, int n_freqs, float* __restrict__ F, int ld, double* __restrict__ bad) {
   pdl_wait();
   int t = blockIdx.x;
   float* o = F + (size_t)t * ld;
@@ -308,6 +335,10 @@ static __global__ void k_mask_features(Geo g, PxRange rg, const float* __restric
     int ch = j / embed_dim, e = j - ch * embed_dim;
     float val = rgb[((long long)b * 3 + ch) * per + rem];
     long long idx = (long long)val;                 // .long(): truncation toward zero
+    if (idx < 0 || idx >= n_vocab) {                // the reference raises IndexError here (nn.Embedding, model/planar.py:344)
+      if (e == 0) atomicAdd(bad, 1.0);
+      idx = idx < 0 ? 0 : n_vocab - 1;
+    }
     o[j] = embed[idx * embed_dim + e];
   }
   float x, y;
@@ -510,6 +541,7 @@ struct LossArgs {
   const float* masks;          // [batch,1,rows,w] (disk only)
   float* rgb_pred;             // optional [n_total,3]
   float* mask_pred;            // optional [n_total]
+  const double* bad_index;     // optional: the handle's sticky bad-colour-index counter, copied to sums[MARF_BAD_INDEX]
 };
 
 __device__ __forceinline__ void block_sum_atomic(double v, double* dst, double* red /*[32]*/) {
@@ -562,6 +594,7 @@ static __global__ void k_loss_stats(Geo g, PxRange rg, LossArgs a, double* __res
     block_sum_atomic(n_mask, &sums[MARF_N_MASK], red);
   }
   block_sum_atomic(bad, &sums[MARF_NONFINITE], red);
+  if (a.bad_index && rg.first == 0 && blockIdx.x == 0 && threadIdx.x == 0) sums[MARF_BAD_INDEX] = *a.bad_index;
 }
 
 // static mask sum (disk masks): N_RGB = 3 * sum m over the local shard

@@ -33,7 +33,7 @@ class PlanarEngine:
     def __init__(self, *, H, W, patch_H, patch_W, batch_size, layers: Sequence[int], skip: Sequence[int] = (),
                  L_2D: Optional[int] = 8, barf_c2f=None, mask_mode=L.MASK_NONE, use_edges=False, use_cropped=True,
                  mask_layers: Sequence[int] = (256, 256, 256, 256, 1), mask_uv_freqs=10, mask_embed_dim=128,
-                 edge_label_channels=1, precision="fp32", device=None, rank=0, world=1, max_chunk_pixels=0):
+                 edge_label_channels=1, precision="fp32", device=None, rank=0, world=1, max_chunk_pixels=0, n_vocab=1500):
         if not torch.cuda.is_available():
             raise RuntimeError("marf_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.lib = L.load()
@@ -75,6 +75,7 @@ class PlanarEngine:
         cfg.use_edges = int(self.use_edges)
         cfg.edge_label_channels = edge_label_channels
         cfg.max_chunk_pixels = int(max_chunk_pixels)
+        cfg.mask_n_vocab = int(n_vocab)
         self.cfg = cfg
         handle = C.c_void_p()
         rc = self.lib.marf_create(C.byref(cfg), C.byref(handle))
@@ -214,6 +215,19 @@ class PlanarEngine:
         io.rgb = out.data_ptr()
         L.check(self.lib, self.handle, self.lib.marf_render(self.handle, C.byref(io), self._stream()), "marf_render")
         return out
+
+    def forward_points(self, mlp_w: List[torch.Tensor], mlp_b: List[torch.Tensor], xy: torch.Tensor, progress=0.0) -> torch.Tensor:
+        """NeuralImageFunction.forward(coord_2d) (model/planar.py:429-449) for explicit, already warped coordinates
+        xy [...,2] -> rgb [...,3] through marf_forward_points."""
+        shape = tuple(xy.shape[:-1])
+        flat = xy.reshape(-1, 2).to(device=self.device, dtype=torch.float32).contiguous()
+        n = flat.shape[0]
+        out = torch.empty(n, 3, dtype=torch.float32, device=self.device)
+        aw, ab = L.ptr_array(list(mlp_w)), L.ptr_array(list(mlp_b))
+        L.check(self.lib, self.handle,
+                self.lib.marf_forward_points(self.handle, aw, ab, flat.data_ptr(), n, float(progress), out.data_ptr(), self._stream()),
+                "marf_forward_points")
+        return out.view(*shape, 3)
 
     def sl3_to_SL3(self, warp: torch.Tensor) -> torch.Tensor:
         self._chk(warp, torch.float32, "warp")

@@ -68,11 +68,13 @@ class NeuralImageFunction(torch.nn.Module):
 
     @torch.no_grad()
     def forward(self, coord_2d=None, *, crop=False, warp=None, n_patches=1):
-        """Forward-only render through marf_render.  The reference passes an explicit grid; here the grid is
-        analytic: `crop` selects get_normalized_pixel_grid(crop=...), `warp` optional per-patch sl(3) parameters."""
-        if coord_2d is not None:
-            raise NotImplementedError("explicit coordinates: use crop=/warp= (the grid is generated on device)")
+        """model/planar.py:429-449.  With `coord_2d` [...,2] (the reference's signature: already warped normalised
+        coordinates) -> rgb [...,3] through marf_forward_points.  Without it the grid is generated on device (marf_render):
+        `crop` selects get_normalized_pixel_grid(crop=...), `warp` optional per-patch sl(3) parameters."""
         ws, bs = self.weights()
+        if coord_2d is not None:
+            return self._engine.forward_points([w.detach() for w in ws], [b.detach() for b in bs], coord_2d,
+                                               progress=float(self.progress))
         return self._engine.render([w.detach() for w in ws], [b.detach() for b in bs], crop=crop, warp=warp,
                                    n_patches=n_patches, progress=float(self.progress))
 
@@ -186,7 +188,7 @@ class Graph(torch.nn.Module):
             barf_c2f=tuple(opt.barf_c2f) if opt.barf_c2f else None, mask_mode=self._mask_mode(),
             use_edges=bool(opt.use_edges), use_cropped=bool(opt.use_cropped_images),
             precision=opt.get("precision", "fp32") or "fp32", device=dev, rank=rank, world=world,
-            max_chunk_pixels=int(opt.get("max_chunk_pixels", 0) or 0))
+            max_chunk_pixels=int(opt.get("max_chunk_pixels", 0) or 0), n_vocab=int(opt.get("N_vocab", 1500) or 1500))
         self.neural_image._engine = self.engine
         ps = self.step_params()
         total = sum(p.numel() for p in ps)
@@ -205,17 +207,30 @@ class Graph(torch.nn.Module):
         #  -> gradients over peer memory up to 4 ranks; the 64-byte loss sums (pure latency) over peer memory at any size)
         peer_max = int(os.environ.get("MARF_PEER_ALLREDUCE_MAX_WORLD", "4"))
         self._peer_grads = False
-        if self._dp() and 1 < world <= 8 and not os.environ.get("MARF_NCCL_ALLREDUCE"):
-            try:
-                from .peer import PeerAllReduce
-                self._peer = PeerAllReduce(dev, total)
+        if self._dp():
+            # replicas must start identical whatever each rank's RNG did (e.g. --seed= gives every rank its own seed)
+            for prm in self.parameters():
+                dist.broadcast(prm.data, src=0)
+            # the peer path needs every rank on one NVLink box, and every rank must take the same path: agree collectively
+            one_box = int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world
+            want = 1 < world <= 8 and one_box and not os.environ.get("MARF_NCCL_ALLREDUCE")
+            peer = None
+            if want:
+                try:
+                    from .peer import PeerAllReduce
+                    peer = PeerAllReduce(dev, total)
+                except Exception as ex:            # pylint: disable=broad-except
+                    print(f"[marf_b200] rank {rank}: peer all-reduce unavailable ({ex!r})", flush=True)
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 1:
+                self._peer = peer
                 self._peer_grads = world <= peer_max
                 if self._peer_grads:
                     self._step_grad_views = [self._peer.grad_local[a:b].view(shape) for a, b, shape in self._grad_slices]
                 self.engine.sums = self._peer.sums
-            except Exception as ex:            # pylint: disable=broad-except
-                print(f"[marf_b200] peer all-reduce unavailable ({ex!r}); using NCCL", flush=True)
-                self._peer, self._peer_grads, self._step_grad_views = None, False, self._grad_views
+            elif want and rank == 0:
+                print("[marf_b200] peer all-reduce not available on every rank; all ranks use NCCL", flush=True)
         e = self.engine
         self._rgb_pred = torch.zeros(e.batch, e.rows * e.w, 3, dtype=torch.float32, device=dev)
         self._mask_pred = torch.zeros(e.batch, e.rows * e.w, 1, dtype=torch.float32, device=dev) \
@@ -458,7 +473,7 @@ class Model(torch.nn.Module):
         if not self._is_main():
             return None
         path = path or self.checkpoint_path()
-        ck = dict(version=1, it=self.it, graph_it=self.graph.it, graph=self.graph.state_dict())
+        ck = dict(version=2, it=self.it, graph_it=self.graph.it, vis_it=self.vis_it, graph=self.graph.state_dict())
         if self.fused_tail is not None:
             ft = self.fused_tail
             ck["fused_adam"] = dict(step=ft.step_count, exp_avg=[t.clone() for t in ft.exp_avg], exp_avg_sq=[t.clone() for t in ft.exp_avg_sq])
@@ -471,12 +486,22 @@ class Model(torch.nn.Module):
 
     def load_checkpoint(self, path, resume=True):
         """resume=True: also optimizer state and iteration counters (continue the run); False: parameters only."""
-        ck = torch.load(path, map_location=self.opt.device, weights_only=False)
+        ck = torch.load(path, map_location=self.opt.device, weights_only=True)     # tensors, ints and dicts only
         self.graph.load_state_dict(ck["graph"])
+        # cached derived inputs (mask-head features gathered from embedding_view) belong to the old parameters
+        self.graph._local = None
+        if self.graph.engine is not None:
+            self.graph.engine.bump_data_version()
         if not resume:
+            # parameters only: the schedule restarts (the checkpoint's `progress` would open the c2f bands at iteration 0)
+            self.graph.neural_image.progress.data.fill_(0.0)
             return 0
         self.it, self.graph.it = int(ck["it"]), int(ck["graph_it"])
+        self.vis_it = int(ck.get("vis_it", 0))
         self.graph.neural_image.progress.data.fill_(self.it / self.opt.max_iter)
+        if (self.fused_tail is not None) != ("fused_adam" in ck):
+            print(f"[marf_b200] WARNING: checkpoint holds {'fused' if 'fused_adam' in ck else 'torch.optim'} Adam state but this run "
+                  f"uses {'--fused_optimizer' if self.fused_tail is not None else 'torch.optim'}: the moments restart from zero", flush=True)
         if self.fused_tail is not None and "fused_adam" in ck:
             ft, st = self.fused_tail, ck["fused_adam"]
             ft.step_count = int(st["step"])
@@ -575,8 +600,14 @@ class Model(torch.nn.Module):
         return loss
 
     def check_finite(self):
-        bad = float(self.graph._sums[L.NONFINITE])
+        """The reference's per-step asserts (model/planar.py:181-182) and the IndexError its colour embedding raises for
+        indices outside the table (model/planar.py:344), from the counters the step left on the device."""
+        sums = self.graph._sums.cpu()
+        bad, idx = float(sums[L.NONFINITE]), float(sums[L.BAD_INDEX])
         assert bad == 0.0, f"{int(bad)} non-finite predictions in the last step (loss is Inf/NaN)"
+        if idx != 0.0:
+            raise IndexError(f"{int(idx)} colour indices trunc(rgb) outside the embedding table (index out of range in self); "
+                             "precision=bf16 serves images in [0,2) only")
 
     @torch.no_grad()
     def predict_entire_image(self):

@@ -19,9 +19,8 @@ def make_engine(cfg: po.PlanarConfig, precision="fp32", rank=0, world=1, max_chu
                         precision=precision, device="cuda:0", rank=rank, world=world, max_chunk_pixels=max_chunk_pixels)
 
 
-def run_step(eng: PlanarEngine, cfg: po.PlanarConfig, params: po.PlanarParams, images: dict, it: int, progress: float,
-             two_phase=False):
-    """Returns dict(rgb_pred, mask_pred, edge_pred, grads{...}, losses{...}) on the CPU."""
+def step_kwargs(eng: PlanarEngine, cfg: po.PlanarConfig, params: po.PlanarParams, images: dict, it: int, progress: float):
+    """Device copies of a case's parameters / inputs and fresh output tensors: the keyword arguments of PlanarEngine.step."""
     dev = eng.device
     cu = lambda t: None if t is None else t.detach().to(dev).contiguous()
     mlp_w = [cu(t) for t in params.mlp_w]
@@ -41,13 +40,23 @@ def run_step(eng: PlanarEngine, cfg: po.PlanarConfig, params: po.PlanarParams, i
     mask_pred = torch.zeros(B, h * w, 1, device=dev) if implicit else None
     edge_pred = torch.zeros(B, 3, h, w, dtype=torch.float64, device=dev) if cfg.use_edges else None
     coef = po.loss_coefficients(cfg, it)
-    kw = dict(mlp_w=mlp_w, mlp_b=mlp_b, warp=warp, rgb=cu(images["rgb"]),
-              masks=cu(images["masks"]) if cfg.use_masks and not implicit else None,
-              masks_eroded=cu(images["masks_eroded"]) if cfg.use_masks and not implicit and cfg.use_edges else None,
-              edges=cu(images["edges"]) if cfg.use_edges else None,
-              mask_w=mask_w, mask_b=mask_b, embed=embed, g_mlp_w=g_mlp_w, g_mlp_b=g_mlp_b, g_warp=g_warp,
-              g_mask_w=g_mask_w, g_mask_b=g_mask_b, rgb_pred=rgb_pred, mask_pred=mask_pred, edge_pred=edge_pred,
-              progress=progress, coef=coef)
+    return dict(mlp_w=mlp_w, mlp_b=mlp_b, warp=warp, rgb=cu(images["rgb"]),
+                masks=cu(images["masks"]) if cfg.use_masks and not implicit else None,
+                masks_eroded=cu(images["masks_eroded"]) if cfg.use_masks and not implicit and cfg.use_edges else None,
+                edges=cu(images["edges"]) if cfg.use_edges else None,
+                mask_w=mask_w, mask_b=mask_b, embed=embed, g_mlp_w=g_mlp_w, g_mlp_b=g_mlp_b, g_warp=g_warp,
+                g_mask_w=g_mask_w, g_mask_b=g_mask_b, rgb_pred=rgb_pred, mask_pred=mask_pred, edge_pred=edge_pred,
+                progress=progress, coef=coef)
+
+
+def run_step(eng: PlanarEngine, cfg: po.PlanarConfig, params: po.PlanarParams, images: dict, it: int, progress: float,
+             two_phase=False, sync=True):
+    """Returns dict(rgb_pred, mask_pred, edge_pred, grads{...}, losses{...}) on the CPU."""
+    kw = step_kwargs(eng, cfg, params, images, it, progress)
+    implicit = cfg.use_implicit_mask
+    coef = kw["coef"]
+    g_mlp_w, g_mlp_b, g_warp, g_mask_w, g_mask_b = kw["g_mlp_w"], kw["g_mlp_b"], kw["g_warp"], kw["g_mask_w"], kw["g_mask_b"]
+    rgb_pred, mask_pred, edge_pred = kw["rgb_pred"], kw["mask_pred"], kw["edge_pred"]
     if two_phase:
         eng.step_forward(**kw)
         eng.step_backward()

@@ -146,3 +146,26 @@ def test_merged_launches_match_the_separate_kernels(env, monkeypatch):
     a = _run("implicit_edges", monkeypatch, {})
     b = _run("implicit_edges", monkeypatch, env)
     _same(a, b, 1e-4)
+
+
+@pytest.mark.parametrize("name", ["mid_mask_c2f", "implicit_edges"])
+def test_step_is_graph_capturable(name):
+    """include/marf_b200.h: no entry point of the step synchronises — so one marf_step can be captured into a CUDA graph
+    (a cudaStreamSynchronize or a blocking copy inside it would abort the capture) and replayed with identical results."""
+    import gpu_util
+    cfg, params, images, it, progress, g = cases.build_case(name)
+    eng = gpu_util.make_engine(cfg, "bf16")
+    ref = gpu_util.run_step(eng, cfg, params, images, it, progress)      # (also warms the data caches)
+    # run_step allocates its tensors outside the capture: build the call's arguments first, capture only the library call
+    kw = gpu_util.step_kwargs(eng, cfg, params, images, it, progress)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.step(**kw)
+    for t in kw["g_mlp_w"] + [kw["g_warp"]]:
+        t.fill_(7.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(kw["g_warp"].cpu(), ref["grads"]["gwarp"])
+    assert torch.equal(kw["g_mlp_w"][1].cpu(), ref["grads"]["gW1"])
+    eng.close()

@@ -147,3 +147,61 @@ def test_edges_match_opencv_golden():
     e1 = eng.compute_edges(rgb[:, :1].contiguous().cuda()).cpu().numpy()
     np.testing.assert_allclose(e1, g["edges1"], rtol=0, atol=1e-12)
     eng.close()
+
+
+def test_warp_points_matches_reference_golden():
+    """marf_warp_points (Warp.warp_grid, warp.py:70-81) against the reference's own output (unit_geometry.npz["warped"])."""
+    import gpu_util
+    g = cases.load_golden("unit_geometry")
+    cfg = po.PlanarConfig(H=40, W=56, patch_H=20, patch_W=28, batch_size=6, use_masks=False)
+    eng = gpu_util.make_engine(cfg, "fp32")
+    h = torch.from_numpy(g["h"]).cuda()
+    xy = torch.from_numpy(g["grid_crop"]).cuda().repeat(6, 1, 1).contiguous()
+    out = eng.warp_points(xy, h).cpu().numpy()
+    np.testing.assert_allclose(out, g["warped"], rtol=0, atol=3e-7)
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_points_matches_oracle(precision):
+    """marf_forward_points = NeuralImageFunction.forward(coord_2d) (model/planar.py:429-449) at arbitrary coordinates,
+    more points than one pass holds, odd count."""
+    import fixtures as fx
+    import gpu_util
+    cfg = po.PlanarConfig(H=72, W=96, patch_H=36, patch_W=48, batch_size=3, barf_c2f=(0.0, 0.4))
+    ws, bs = fx.synth_mlp(5, po.layer_shapes(cfg), scale=2.0)
+    eng = gpu_util.make_engine(cfg, precision)
+    gen = torch.Generator().manual_seed(11)
+    n = 70001 if precision == "bf16" else 6001           # (bf16 handles render in passes of 65536 rows)
+    xy = (torch.rand(n, 2, generator=gen) - 0.5) * 1.3
+    out = eng.forward_points([w.cuda() for w in ws], [b.cuda() for b in bs], xy.cuda(), progress=0.3).cpu()
+    ref = po.neural_image(xy, ws, bs, cfg, progress=0.3)
+    assert out.shape == (n, 3)
+    assert (out - ref).abs().max().item() <= OUT_TOL
+    # leading dimensions are kept: [B, P, 2] -> [B, P, 3] as the reference's call at model/planar.py:334
+    out3 = eng.forward_points([w.cuda() for w in ws], [b.cuda() for b in bs], xy[:6000].view(3, 2000, 2).cuda(), progress=0.3)
+    assert out3.shape == (3, 2000, 3) and torch.equal(out3.cpu().view(-1, 3), out[:6000])
+    eng.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_bad_colour_index_is_counted_not_synchronised(precision):
+    """trunc(rgb) outside the embedding table: IndexError in the reference (model/planar.py:344); here a device-side count in
+    loss_sums[MARF_BAD_INDEX], clamped gather, no host synchronisation inside the step."""
+    import gpu_util
+    from marf_b200 import _lib as L
+    cfg, params, images, it, progress, _ = cases.build_case("implicit")
+    eng = gpu_util.make_engine(cfg, precision)
+    res = gpu_util.run_step(eng, cfg, params, images, it, progress)
+    assert float(eng.sums[L.BAD_INDEX]) == 0.0 and res["nonfinite"] == 0.0
+    bad = dict(images)
+    bad["rgb"] = images["rgb"].clone()
+    bad["rgb"][1, 2, 5, 7] = 1600.0 if precision == "fp32" else 2.5
+    bad["rgb"][0, 0, 3, 3] = -1.5
+    eng.bump_data_version()
+    gpu_util.run_step(eng, cfg, params, bad, it, progress)
+    assert float(eng.sums[L.BAD_INDEX]) == 2.0
+    eng.bump_data_version()
+    gpu_util.run_step(eng, cfg, params, images, it, progress)
+    assert float(eng.sums[L.BAD_INDEX]) == 0.0
+    eng.close()
