@@ -32,6 +32,12 @@ FLOP_PER_PX = {  # algorithmic: 2 * MACs of fwd + dX + dW
 
 
 def workload(name, n_gpus):
+    wl = _workload(name, n_gpus)
+    wl["batch_per_gpu"] = wl["batch"] // n_gpus if wl["scaling"] == "strong" else wl["batch"] // n_gpus
+    return wl
+
+
+def _workload(name, n_gpus):
     if name == "config2":
         return dict(name="config2: planar.yaml full posenc + implicit mask network + edge term, synthetic 360x480, "
                          f"{5 * n_gpus} patches 180x240 ({5} per GPU)",
@@ -107,63 +113,82 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def roofline_lines(wl, kern, pk, rows_per_gpu, step_tflops, args):
-    """`roofline` = the dominant kernel (largest share of the step) against the roofline that bounds it, from the live
-    per-launch durations of the per-kernel pass; `kernels` lists all five tensor-core kernel classes the same way;
-    `step_roofline` keeps the whole-step figure (algorithmic FLOP of the step / step time vs the tensor peak).
-    Algorithmic bytes / FLOP per pixel-sample row (h = hidden layers, all 256 wide, two chains when
-    the mask head is on):
-      k_tc_dw          : reads X_l and dY_l of every 256x256 layer (1024 B), of the output layers (X 512 B + dlogits tile 16 B)
-                         and of layer 0 (dY_0 512 B + 64-wide input 128 B)
-      k_tc_chain<fwd>  : reads the 64-wide input (128 B), writes 4 activations (2048 B) + 4 mask-bit rows (128 B) + logits (16 B)
-      k_tc_chain<dx>   : reads the dlogits tile (16 B) + 4 mask-bit rows (128 B), writes 4 dY (2048 B)
-      k_tc_gemm<64,wg> : reads dY_0 (512 B)
-    traffic (DRAM bytes per launch from ncu) is read from profiles/r01_kernel_traffic.json when it holds this workload."""
-    out = {}
-    peak_t = pk["bf16_sustained"]
-    out["step_roofline"] = dict(bound="tensor", achieved=step_tflops, peak=peak_t * args.gpus, unit="TFLOP/s",
-                                frac=step_tflops / (peak_t * args.gpus),
-                                note="algorithmic FLOP of the whole step / mean step time, all kernels; peak = sustained bf16")
-    if not kern:
-        out["roofline"] = dict(out["step_roofline"], traffic=None, peak_source=pk["source"])
-        return out
+def kernel_tables(wl):
+    """Algorithmic FLOP and HBM bytes per pixel-sample row of every tensor-core kernel class (SURVEY.md
+    section 8a/8d: 2 * MACs, unpadded; coordinates are analytic so the step's only inputs are the targets / masks).
+      k_tc_chain<fwd>  : 64-wide input in (128 B), 4 activations (2048 B) + 4 mask-bit rows (128 B) + logits (16 B) out
+      k_tc_bwd         : every X_l once (dW), the dlogits tiles, the mask bits; dY_0 of the image chain out (warp-gradient
+                         GEMM); the dY_l hand-over between its chain pairs and dW pairs goes through L2, not counted
+      k_tc_chain<dx> / k_tc_dw : the two halves of k_tc_bwd as separate launches (MARF_NO_BWD_FUSE, 512-wide networks)
+      k_tc_gemm<64,wg> : reads dY_0 (512 B)"""
     chains = 2 if wl["implicit"] else 1
     width = wl["layers"][0]
     hidden = len(wl["layers"]) - 1
-    rows = (rows_per_gpu + 127) // 128 * 128
+    k0 = 2 + 4 * wl["L"]
+    out_w = [3, 1][:chains]
+    f_fwd = sum(2 * ((k0 if c == 0 else 42 + 384) * width + (hidden - 1) * width * width + width * out_w[c]) for c in range(chains))
+    f_dx = sum(2 * ((hidden - 1) * width * width + width * out_w[c]) for c in range(chains)) + 2 * k0 * width     # + dX0 of the image MLP
+    f_dw = f_fwd
     byt = {"k_tc_dw": chains * ((hidden - 1) * 4 * width + (2 * width + 16) + (2 * width + 128)),
            "k_tc_chain<fwd>": chains * (128 + hidden * 2 * width + hidden * width // 8 + 16),
            "k_tc_chain<dx>": chains * (16 + hidden * width // 8 + hidden * 2 * width),
            "k_tc_gemm<64,warp_grad>": 2 * width}
-    flop = {"k_tc_dw": chains * 2 * ((hidden - 1) * width * width + width * (3 if chains == 1 else 2) + width * 64),
-            "k_tc_chain<fwd>": chains * 2 * (64 * width + (hidden - 1) * width * width + width * (3 if chains == 1 else 2)),
-            "k_tc_chain<dx>": chains * 2 * (64 * width + (hidden - 1) * width * width),
-            "k_tc_gemm<64,warp_grad>": 2 * width * 64}
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
-    if os.path.exists(tp):
-        tj = json.load(open(tp))
-        if tj.get("workload") == args.workload and tj.get("precision") == args.precision:
-            traffic = tj["dram_bytes_per_launch"]
+    byt["k_tc_bwd"] = chains * (hidden * 2 * width + 128 + 2 * 16 + hidden * width // 8) + 2 * width
+    flop = {"k_tc_chain<fwd>": f_fwd, "k_tc_dw": f_dw, "k_tc_chain<dx>": f_dx - 2 * k0 * width, "k_tc_gemm<64,warp_grad>": 2 * k0 * width}
+    flop["k_tc_bwd"] = flop["k_tc_dw"] + flop["k_tc_chain<dx>"]
+    return flop, byt
+
+
+def load_traffic(workload_key, precision):
+    """DRAM bytes per launch per kernel from the committed ncu capture (profiles/r02_kernel_traffic.json), when it holds this workload."""
+    for name in ("r02_kernel_traffic.json", "r01_kernel_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            if tj.get("workload") == workload_key and tj.get("precision") == precision:
+                return tj["dram_bytes_per_launch"], name
+    return {}, None
+
+
+def roofline_lines(wl, wl_key, precision, kern, pk, rows_per_gpu, step_tflops, n_gpus):
+    """`roofline` (this path is bounded by the tensor cores): the dominant kernel's ALGORITHMIC FLOP per launch /
+    its mean launch duration (CUDA events on the launching stream, per-kernel pass) against the measured bf16 peak (burst: the
+    stricter denominator), with the algorithmic bytes and the DRAM traffic of the ncu capture beside it so that the waste ratio
+    is in the record; `hbm_view` = the same launch against the HBM roofline; `kernels` = every tensor-core kernel class;
+    `step_roofline` = algorithmic FLOP of the whole step / step time."""
+    out = {}
+    burst, sust = pk["bf16_burst"], pk["bf16_sustained"]
+    out["step_roofline"] = dict(bound="tensor", achieved=step_tflops, peak=burst * n_gpus, unit="TFLOP/s", frac=step_tflops / (burst * n_gpus),
+                                frac_of_sustained=step_tflops / (sust * n_gpus),
+                                note="algorithmic FLOP of the whole step / mean step time, all kernels; peak = measured burst bf16")
+    if not kern:
+        out["roofline"] = dict(out["step_roofline"], traffic=None, peak_source=pk["source"])
+        return out
+    flop, byt = kernel_tables(wl)
+    rows = (rows_per_gpu + 127) // 128 * 128
+    traffic, tsrc = load_traffic(wl_key, precision)
     rowsets = []
     for k, v in kern.items():
         us = v["us_per_launch"]
         n_l = max(1.0, v["launches_per_step"])
-        gbs = byt[k] * rows / n_l / (us * 1e-6) / 1e9
+        alg_bytes = byt[k] * rows / n_l
+        gbs = alg_bytes / (us * 1e-6) / 1e9
         tf = flop[k] * rows / n_l / (us * 1e-6) / 1e12
-        hbm_bound = gbs / pk["hbm"] >= tf / peak_t
-        rowsets.append(dict(kernel=k, us_per_launch=us, launches_per_step=v["launches_per_step"],
-                            bound="hbm" if hbm_bound else "tensor",
-                            achieved=gbs if hbm_bound else tf, peak=pk["hbm"] if hbm_bound else peak_t,
-                            unit="GB/s" if hbm_bound else "TFLOP/s", frac=(gbs / pk["hbm"]) if hbm_bound else (tf / peak_t),
-                            hbm_gbs=gbs, tensor_tflops=tf, traffic=traffic.get(k)))
+        tr = traffic.get(k)
+        rowsets.append(dict(kernel=k, us_per_launch=us, launches_per_step=v["launches_per_step"], bound="tensor",
+                            achieved=tf, peak=burst, unit="TFLOP/s", frac=tf / burst, frac_of_sustained=tf / sust,
+                            algorithmic_bytes=alg_bytes, traffic=tr, traffic_over_algorithmic=(tr / alg_bytes) if tr else None,
+                            hbm_view=dict(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"],
+                                          traffic_gbs=(tr / (us * 1e-6) / 1e9) if tr else None)))
     rowsets.sort(key=lambda r: -r["us_per_launch"] * r["launches_per_step"])
     dom = rowsets[0]
-    out["roofline"] = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"],
-                           traffic=dom["traffic"], kernel=dom["kernel"], us_per_launch=dom["us_per_launch"],
-                           peak_source=pk["source"] + (", HBM copy bandwidth" if dom["bound"] == "hbm" else ", sustained bf16"),
-                           note="dominant kernel of the step; achieved = algorithmic bytes (or FLOP) per launch / mean launch "
-                                "duration from CUDA events on the launching stream (per-kernel pass, L2 flushed between steps)")
+    out["roofline"] = dict(bound="tensor", achieved=dom["achieved"], peak=dom["peak"], unit="TFLOP/s", frac=dom["frac"],
+                           frac_of_sustained=dom["frac_of_sustained"], traffic=dom["traffic"], algorithmic_bytes=dom["algorithmic_bytes"],
+                           traffic_over_algorithmic=dom["traffic_over_algorithmic"], hbm_view=dom["hbm_view"],
+                           kernel=dom["kernel"], us_per_launch=dom["us_per_launch"],
+                           peak_source=pk["source"] + ", burst bf16 (cuBLAS 8192^3 best of 10)", traffic_source=tsrc,
+                           note="dominant kernel of the step; achieved = algorithmic FLOP per launch / mean launch duration from CUDA "
+                                "events on the launching stream (per-kernel pass, L2 flushed between steps)")
     out["kernels"] = rowsets
     return out
 
@@ -244,15 +269,28 @@ def eager_gpu_reference(wl, device, steps=5, warmup=3):
                      f"on the same GPU, whole workload ({n_px} pixel-samples per step), {steps} timed steps")
 
 
+def cpu_sample_patches(wl):
+    """Patches per step of the CPU arm: the whole workload when it is small (config 2: 5 patches, 216,000 pixel-samples), else a
+    bounded sample of about one million pixel-samples (config 4: one 1024x1024 patch; ~4 s per step on the box's host cores)."""
+    per = wl["patch_H"] * wl["patch_W"]
+    return max(1, min(wl["batch_per_gpu"], (1 << 20) // per))
+
+
 def run_reference(args):
+    """The reference arm: the reference's own op sequence (oracle port, eager PyTorch fp32 + autograd) on the host cores, on the same
+    workload / metric / unit.  Rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = workload(args.workload, args.gpus)
-    steps = max(1, min(args.steps, 20))
-    base, n_px = cpu_reference(wl, steps=steps, warmup=min(args.warmup, 2), patches=1)
+    patches = cpu_sample_patches(wl)
+    warm = min(args.warmup, 3)
+    # keep the whole arm within a few minutes: time one step, then size the timed loop
+    probe, n_px = cpu_reference(wl, steps=1, warmup=0, patches=patches)
+    steps = max(1, min(args.steps, int(150.0 / max(probe["ms_per_step"] * 1e-3, 1e-3)) - warm))
+    base, n_px = cpu_reference(wl, steps=steps, warmup=warm, patches=patches)
     line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=base["value"], unit="pixel-samples/s", impl="reference",
-                n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2), ms_per_step=base["ms_per_step"], higher_is_better=True,
+                n_gpus=args.gpus, steps=steps, warmup=warm, ms_per_step=base["ms_per_step"], higher_is_better=True,
                 scaling=wl["scaling"], vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=wl["name"], sample=base["sample"]),
                 cpu_baseline=dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port", sample=base["sample"]),
@@ -261,26 +299,17 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_marf(args):
+def measure(wl_key, precision, args, ctx, steps, warmup, e2e=True, kernels=True, sampler=None):
+    """One workload through the library: resident-input `value`, `e2e` through Model.train_iteration with host buffers, and the
+    per-kernel pass.  Returns a dict; frees the model afterwards."""
     import torch
     import torch.distributed as dist
-    from marf_b200 import _lib as L
     from marf_b200 import planar
     from marf_b200.attrdict import AttrDict
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
-    torch.cuda.set_device(local)
-    device = f"cuda:{local}"
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(device))
-    wl = workload(args.workload, args.gpus)
+    world, rank, device, flush = ctx["world"], ctx["rank"], ctx["device"], ctx["flush"]
+    wl = workload(wl_key, args.gpus)
     out_dir = os.path.join("/tmp", f"marf_bench_{os.getpid()}")
-    opt = make_opt(wl, device, args.precision, out_dir)
+    opt = make_opt(wl, device, precision, out_dir)
     os.makedirs(out_dir, exist_ok=True)
     torch.manual_seed(3)
     m = planar.Model(opt)
@@ -292,7 +321,6 @@ def run_marf(args):
     g = m.graph
     var = AttrDict(idx=torch.arange(opt.batch_size), images=m.images)
     n_px_total = opt.batch_size * wl["patch_H"] * wl["patch_W"]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)       # > 126 MB L2
     st = torch.cuda.current_stream()
 
     def barrier():
@@ -301,18 +329,17 @@ def run_marf(args):
         torch.cuda.synchronize()
 
     # ---------------- resident-input arm: marf_step (+ allreduce) only
-    for _ in range(max(3, args.warmup)):
+    for _ in range(max(3, warmup)):
         g.forward(var, mode="train")
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:                                       # (one nvidia-smi poller per job, not one per rank)
+    if sampler is not None and rank == 0:                 # (one nvidia-smi poller per job, not one per rank)
         sampler.start()
-    time.sleep(0.1)
+        time.sleep(0.1)
     launches0 = g.engine.launches
     evs = []
     barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the event pair)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(st)
@@ -326,78 +353,85 @@ def run_marf(args):
     t = torch.tensor([dev_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t)
-    ms_per_step = dev_ms / args.steps
-    value = n_px_total / (ms_per_step * 1e-3)
+    ms_per_step = float(t) / steps
+    res = dict(workload=wl["name"], precision=precision, value=n_px_total / (ms_per_step * 1e-3), ms_per_step=ms_per_step, steps=steps,
+               pixel_samples_per_step=n_px_total, flop_per_pixel_sample=wl["flop"], gpu_launches=launches, wall_s_timed_loop=wall)
+    res["tflops"] = res["value"] * wl["flop"] / 1e12
 
     # ---------------- e2e arm: plugin call with host buffers (H2D of targets, D2H of the loss) + Adam
-    e = g.engine
-    loc = g._local[1]                                   # this rank's shard of the resident inputs (what the step reads)
-    host = {k: v.cpu().pin_memory() for k, v in dict(rgb=loc.rgb).items()}
-    h2d = sum(v.numel() * v.element_size() for v in host.values()) * world     # whole job, bytes per step
-    d2h = 8 * world
+    if e2e:
+        loc = g._local[1]                                   # this rank's shard of the resident inputs (what the step reads)
+        host = {k: v.cpu().pin_memory() for k, v in dict(rgb=loc.rgb).items()}
+        h2d = sum(v.numel() * v.element_size() for v in host.values()) * world     # whole job, bytes per step
+        d2h = 8 * world
+        # Input prefetch, as a training data loader does it: the targets of step i+1 are copied host->device on a copy stream into
+        # the second of two device buffers while step i computes (every step's H2D copy is inside the timed region; a buffer is
+        # refilled only after the step that read it has finished).  The loss of every step is read back (D2H into pinned
+        # memory); the host consumes it two steps later so that Python/launch overhead overlaps the GPU's work on the next steps.
+        copy_st = torch.cuda.Stream(device=device)
+        bufs = [loc.rgb, torch.empty_like(loc.rgb)]
+        ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
+        ev_free = [torch.cuda.Event(), torch.cuda.Event()]
+        for ev in ev_free:
+            ev.record(st)
+        LAG = 2                                             # the host reads step i's loss while steps i+1, i+2 are queued
+        loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(LAG + 1)]
+        loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
+        seen = []
 
-    # Input prefetch, as a training data loader does it: the targets of step i+1 are copied host->device on a copy stream into
-    # the second of two device buffers while step i computes (every step's H2D copy is inside the timed region; a buffer is
-    # refilled only after the step that read it has finished).  The loss of every step is read back (D2H into pinned
-    # memory); the host consumes it two steps later so that Python/launch overhead overlaps the GPU's work on the next steps.
-    copy_st = torch.cuda.Stream(device=device)
-    bufs = [loc.rgb, torch.empty_like(loc.rgb)]
-    ev_copied = [torch.cuda.Event(), torch.cuda.Event()]
-    ev_free = [torch.cuda.Event(), torch.cuda.Event()]
-    for ev in ev_free:
-        ev.record(st)
-    LAG = 2                                             # the host reads step i's loss while steps i+1, i+2 are queued
-    loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(LAG + 1)]
-    loss_ev = [torch.cuda.Event() for _ in range(LAG + 1)]
-    seen = []
+        def prefetch(i):
+            with torch.cuda.stream(copy_st):
+                copy_st.wait_event(ev_free[i & 1])
+                bufs[i & 1].copy_(host["rgb"], non_blocking=True)         # H2D of step i's targets (this rank's shard)
+                ev_copied[i & 1].record(copy_st)
 
-    def prefetch(i):
-        with torch.cuda.stream(copy_st):
-            copy_st.wait_event(ev_free[i & 1])
-            bufs[i & 1].copy_(host["rgb"], non_blocking=True)         # H2D of step i's targets (this rank's shard)
-            ev_copied[i & 1].record(copy_st)
+        def e2e_step(i):
+            st.wait_event(ev_copied[i & 1])
+            loc.rgb = bufs[i & 1]
+            g.engine.bump_data_version()                    # genuinely new data every step: cached derived inputs are rebuilt
+            prefetch(i + 1)
+            loss = m.train_iteration(var, None)
+            ev_free[i & 1].record(st)
+            if opt.warp.fix_first and m.fused_tail is None:
+                g.warp_param.weight.data[0] = 0
+            k = i % (LAG + 1)
+            loss_host[k].copy_(loss.all.detach().reshape(1), non_blocking=True)       # D2H of the step's result
+            loss_ev[k].record(st)
+            if i >= LAG:
+                j = (i - LAG) % (LAG + 1)
+                loss_ev[j].synchronize()
+                seen.append(float(loss_host[j]))
 
-    def e2e_step(i):
-        st.wait_event(ev_copied[i & 1])
-        loc.rgb = bufs[i & 1]
-        prefetch(i + 1)
-        loss = m.train_iteration(var, None)
-        ev_free[i & 1].record(st)
-        if opt.warp.fix_first and m.fused_tail is None:
-            g.warp_param.weight.data[0] = 0
-        k = i % (LAG + 1)
-        loss_host[k].copy_(loss.all.detach().reshape(1), non_blocking=True)       # D2H of the step's result
-        loss_ev[k].record(st)
-        if i >= LAG:
-            j = (i - LAG) % (LAG + 1)
-            loss_ev[j].synchronize()
-            seen.append(float(loss_host[j]))
-
-    prefetch(0)
-    for i in range(3):
-        e2e_step(i)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(st)
-    for i in range(args.steps):
-        e2e_step(i + 3)
-    e1.record(st)
-    barrier()
-    assert all(v == v for v in seen) or os.environ.get("MARF_CHAIN_DBG"), "non-finite loss in the e2e arm"
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t) / args.steps
-    e2e_value = n_px_total / (e2e_ms * 1e-3)
-    clocks = sampler.stop()                              # sampled over both timed loops (resident + e2e)
+        prefetch(0)
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for i in range(steps):
+            e2e_step(i + 3)
+        e1.record(st)
+        barrier()
+        assert all(v == v for v in seen) or os.environ.get("MARF_CHAIN_DBG") or os.environ.get("MARF_BWD_DBG"), "non-finite loss in the e2e arm"
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t) / steps
+        res["e2e"] = dict(value=n_px_total / (e2e_ms * 1e-3), unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                          ms_per_step=e2e_ms,
+                          what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first); every step's targets are "
+                               "copied from pinned host memory (prefetched on a copy stream during the previous step, double-buffered, "
+                               "data version bumped so cached derived inputs are rebuilt) and the loss is read back every step (consumed "
+                               "two steps later)")
+    if sampler is not None and rank == 0:
+        res["clocks"] = sampler.stop()                       # sampled over both timed loops (resident + e2e)
 
     # ---------------- per-kernel pass (roofline): the same resident-input steps again with CUDA-event pairs recorded on
-    # the launching stream around every launch of the five tensor-core kernel classes (marf_profile).  Separate from
+    # the launching stream around every launch of the tensor-core kernel classes (marf_profile).  Separate from
     # the headline loop because an event between two launches suspends programmatic dependent launch there.
     kern = {}
-    if args.precision == "bf16":
-        ksteps = max(1, min(args.steps, 20))
+    if kernels and precision == "bf16":
+        ksteps = max(1, min(steps, 20))
         g.engine.profile(True)
         g.forward(var, mode="train")
         torch.cuda.synchronize()
@@ -408,34 +442,74 @@ def run_marf(args):
         torch.cuda.synchronize()
         kern = {k: dict(us_per_launch=1e3 * ms / max(n, 1), launches_per_step=n / ksteps) for k, (ms, n) in g.engine.profile_read().items() if n}
         g.engine.profile(False)
+    res["_kern"], res["_wl"] = kern, wl
+    g.engine.close()
+    del m, g, var
+    torch.cuda.empty_cache()
+    return res
 
+
+def run_marf(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local)
+    device = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(device))
+    ctx = dict(world=world, rank=rank, device=device,
+               flush=torch.empty(256 << 20, dtype=torch.uint8, device=device))       # > 126 MB L2
+    sampler = ClockSampler(local)
+    head = measure(args.workload, args.precision, args, ctx, args.steps, args.warmup, sampler=sampler)
+    wl, kern = head.pop("_wl"), head.pop("_kern")
+    pk = peaks()
+    line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=head["value"], unit="pixel-samples/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=max(3, args.warmup), ms_per_step=head["ms_per_step"], higher_is_better=True,
+                scaling=wl["scaling"], vs_baseline=None, dtype="f32" if args.precision == "fp32" else "bf16 (fp32 accumulate)",
+                data="synthetic",
+                config=dict(workload=wl["name"], precision=args.precision, pixel_samples_per_step=head["pixel_samples_per_step"],
+                            flop_per_pixel_sample=wl["flop"], l2="flushed between timed steps (256 MiB memset)",
+                            timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                            wall_s_timed_loop=head["wall_s_timed_loop"]),
+                clocks=head.get("clocks"), e2e=head["e2e"], gpu_launches=head["gpu_launches"])
+    line.update(roofline_lines(wl, args.workload, args.precision, kern, pk, head["pixel_samples_per_step"] // world, head["tflops"], args.gpus))
+    # ---------------- the other named configurations and the fp32 parity mode, same run (N = 1 only: they are single-GPU lines)
+    if args.gpus == 1 and not args.headline_only:
+        short = max(3, min(args.steps, 10))
+        if args.precision == "bf16":
+            try:
+                f = measure(args.workload, "fp32", args, ctx, max(2, min(args.steps, 3)), 1, e2e=False, kernels=False)
+                line["value_fp32"] = f["value"]
+                line["fp32"] = dict(value=f["value"], unit="pixel-samples/s", ms_per_step=f["ms_per_step"], steps=f["steps"],
+                                    what="the same workload with precision=fp32 (the <=1e-3 parity mode, CUDA-core SGEMMs), resident inputs")
+            except Exception as ex:                      # never lose the headline line to an extra
+                line["fp32"] = dict(unavailable=repr(ex)[:200])
+        for extra in ("config2", "config4", "config5"):
+            if extra == args.workload:
+                continue
+            try:
+                r = measure(extra, args.precision, args, ctx, short if extra != "config2" else max(short, min(args.steps, 50)), 3, e2e=True, kernels=True)
+                ewl, ekern = r.pop("_wl"), r.pop("_kern")
+                r.update(roofline_lines(ewl, extra, args.precision, ekern, pk, r["pixel_samples_per_step"], r["tflops"], 1))
+                r.pop("kernels", None)
+                line[extra] = r
+            except Exception as ex:
+                line[extra] = dict(unavailable=repr(ex)[:200])
     if rank == 0:
-        pk = peaks()
-        tflops = value * wl["flop"] / 1e12
-        line = dict(metric="pixel-samples/sec (fwd+bwd+warp grad)", value=value, unit="pixel-samples/s", n_gpus=args.gpus,
-                    steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True,
-                    scaling=wl["scaling"], vs_baseline=None, dtype="f32" if args.precision == "fp32" else "bf16 (fp32 accumulate)",
-                    data="synthetic",
-                    config=dict(workload=wl["name"], precision=args.precision, pixel_samples_per_step=n_px_total,
-                                flop_per_pixel_sample=wl["flop"], l2="flushed between timed steps (256 MiB memset)",
-                                timing="sum of per-step CUDA-event intervals on the launch stream, max over ranks",
-                                wall_s_timed_loop=wall),
-                    clocks=clocks,
-                    e2e=dict(value=e2e_value, unit="pixel-samples/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                             ms_per_step=e2e_ms, what="Model.train_iteration with --fused_optimizer (fused step + device Adam + fix_first); every step's targets are copied "
-                                  "from pinned host memory (prefetched on a copy stream during the previous step, double-buffered) and the "
-                                  "loss is read back every step (consumed two steps later)"),
-                    gpu_launches=launches)
-        line.update(roofline_lines(wl, kern, pk, n_px_total // world, tflops, args))
         if args.gpus == 1 and not args.no_cpu:
-            base, _ = cpu_reference(wl, steps=3, warmup=1, patches=1)
+            base, _ = cpu_reference(wl, steps=3, warmup=1, patches=cpu_sample_patches(wl))
             line["cpu_baseline"] = dict(value=base["value"], unit="pixel-samples/s", cores=base["cores"], kind="port",
                                         sample=base["sample"])
-            if wl["batch"] * wl["patch_H"] * wl["patch_W"] <= 1 << 20:      # (eager autograd keeps every activation in fp32)
-                try:
-                    line["eager_gpu_baseline"] = eager_gpu_reference(wl, device)
-                except Exception as ex:                                      # informational leg: never fail the bench line
-                    line["eager_gpu_baseline"] = dict(unavailable=repr(ex)[:200])
+            try:                                                         # informational leg: never fail the bench line
+                line["eager_gpu_baseline"] = eager_gpu_reference(workload("config2", 1), device)
+            except Exception as ex:
+                line["eager_gpu_baseline"] = dict(unavailable=repr(ex)[:200])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -444,12 +518,13 @@ def run_marf(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="marf", choices=["marf", "reference"])
     ap.add_argument("--precision", default=os.environ.get("MARF_BENCH_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--workload", default=os.environ.get("MARF_BENCH_WORKLOAD", "config4"))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the extra configurations / fp32 leg")
     args = ap.parse_args()
     os.chdir(ROOT)
     if args.impl == "reference":

@@ -230,11 +230,12 @@ int marf_debug_read_bf16(marf_handle* h, int chain, int which, int layer, float*
 
 /* Per-kernel timing for bench.py's roofline line.  While enabled, the bf16 path records a CUDA event pair on the launching
  * stream around every launch of its five tensor-core kernel classes (this suspends programmatic dependent launch across
- * those launches, so enable it for a separate measurement pass, not for the headline timing).  Classes: the two fused
- * chain kernels (forward, dX), the merged dW launch, the dX0 + encoding-backward GEMM.  marf_profile_read
+ * those launches, so enable it for a separate measurement pass, not for the headline timing).  Classes: the fused forward
+ * chain, the fused backward launch (dX chains + every dW GEMM; or, with MARF_NO_BWD_FUSE, the dX chain and the merged dW launch
+ * separately), the dX0 + encoding-backward GEMM.  marf_profile_read
  * synchronises the recorded events, writes per class the summed milliseconds and the launch count, and clears them. */
 #define MARF_PROF_CLASSES 5
-enum { MARF_PROF_CHAIN_FWD = 0, MARF_PROF_CHAIN_DX = 1, MARF_PROF_DW = 2, MARF_PROF_RESERVED = 3, MARF_PROF_DX0 = 4 };
+enum { MARF_PROF_CHAIN_FWD = 0, MARF_PROF_CHAIN_DX = 1, MARF_PROF_DW = 2, MARF_PROF_BWD = 3, MARF_PROF_DX0 = 4 };
 int marf_profile(marf_handle* h, int enable);
 int marf_profile_read(marf_handle* h, double* ms, int64_t* launches, int n_classes);
 

@@ -14,6 +14,7 @@
 #include "fp32_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_chain.cuh"
+#include "tc_bwd.cuh"
 
 namespace marf {
 
@@ -481,6 +482,8 @@ struct Bf16State {
   int num_sms = 148;
   bool table_done = false;                // the class table of this step was written by the fused prologue launch
   bool accs_zeroed = false;               // the prologue launch of the forward pass already zeroed the backward accumulators
+  uint32_t* ready = nullptr;              // k_tc_bwd: [2 chains][4 units][chunk / 128] per-tile hand-over flags (epoch values, never reset)
+  uint32_t epoch = 0;                     // k_tc_bwd launches of this handle so far
   uint32_t* flags_all = nullptr;          // every per-tile flag array of both chains, zeroed before each chained launch
   size_t flags_words = 0, flags_used = 0;
 };
@@ -623,6 +626,7 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1 * 512 + 1) * 4));
   return MARF_OK;
@@ -643,7 +647,8 @@ int bf16_create(marf_handle* h) {
   S->num_sms = prop.multiProcessorCount;
   S->flags_words = (size_t)(h->chunk / 128 + 1) * 4 * MARF_MAX_LAYERS;
   S->flags_all = (uint32_t*)ws_alloc(h, S->flags_words * 4);
-  if (!S->flags_all) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (flags)");
+  S->ready = (uint32_t*)ws_alloc(h, (size_t)2 * tc::kChUnits * (h->chunk / 128 + 1) * 4);
+  if (!S->flags_all || !S->ready) return fail(h, MARF_ERR_CUDA, "bf16 workspace allocation failed (flags)");
   int rc = build_bf_chain(h, S, S->img, h->img, true);
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
@@ -1075,6 +1080,150 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
   return MARF_OK;
 }
 
+
+// ---- the whole backward pass of the fused 256-wide networks in ONE launch (tc_bwd.cuh): the dX chains on the first CTA pairs,
+// every dW / db GEMM on the others, dY handed over tile by tile through L2
+static bool bwd_fused_enabled() {
+  static const bool on = getenv("MARF_NO_BWD_FUSE") == nullptr;
+  return on;
+}
+static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows) {
+  Bf16State* S = h->bf16;
+  ProfScope prof(h, st, MARF_PROF_BWD);
+  tc::BwdJobs jobs{};
+  const int n_tiles = rows / 128;
+  const int total_pairs = S->num_sms / 2;
+  jobs.rows = rows;
+  jobs.chain.n = n_chains;
+  jobs.chain.n_tiles = n_tiles;
+  jobs.chain.ready = S->ready;
+  jobs.chain.epoch = ++S->epoch;
+  jobs.chain.interleave = 1;
+  // dY tiles are stored with evict_last priority (they are consumed out of L2 by this launch) and dropped from L2 without a
+  // write-back once consumed (discard.global.L2): -2.5 % launch time; MARF_BWD_STORE_LAST=0 / MARF_BWD_DISCARD=0 switch them off
+  jobs.chain.store_last = getenv("MARF_BWD_STORE_LAST") ? atoi(getenv("MARF_BWD_STORE_LAST")) : 1;
+  const bool discard = getenv("MARF_BWD_DISCARD") ? atoi(getenv("MARF_BWD_DISCARD")) != 0 : true;
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    tc::ChainJob& J = jobs.chain.c[ci];
+    const int n = B.n;
+    J.bits_ld = 256 / 32;
+    // unit 0: dY[n-2] = (dlogits W_last) * mask(act[n-1]); unit u >= 1: layer l = n-1-u, dY[l-1] = (dY[l] W_l) * mask(act[l])
+    J.tmIn = B.tmDL128;
+    J.tmWout = B.tmWout16;                   // unused
+    for (int u = 0; u < tc::kChUnits; ++u) {
+      const int l = n - 1 - u;
+      J.u[u].tmW = u == 0 ? B.tmWlast64 : B.L[l].tmWt64;
+      J.u[u].tmOut = B.tmDY128[l - 1];
+      J.u[u].bias = nullptr;
+      J.u[u].bits = B.bits[l];
+    }
+  }
+  // dW jobs: a 64-row stage costs a dW pair about the same whatever the job (four MMAs per issuer thread at ~90 cycles of issue
+  // each against 128 / 64 cycles of tensor work for N = 256 / 128): equal weights, slightly less for the 64-wide layer-0 inputs
+  double weight[tc::kBwdMaxJobs];
+  auto add = [&](const CUtensorMap& tmDY, const CUtensorMap& tmX, const uint32_t* ready, int n_cols, int m_valid, int n_valid,
+                 int ld_w, int do_bias, float* dW, float* db) {
+    tc::BwdDwJob& D = jobs.dw[jobs.n_dw];
+    D.tmDY = tmDY; D.tmX = tmX; D.ready = ready; D.n_cols = n_cols; D.m_valid = m_valid; D.n_valid = n_valid;
+    D.ld_w = ld_w; D.do_bias = do_bias; D.dW = dW; D.db = db;
+    weight[jobs.n_dw++] = n_cols == 256 ? 1.0 : 0.8;
+  };
+  for (int ci = 0; ci < n_chains; ++ci) {
+    BfChain& B = *chains[ci];
+    Chain& F = *B.f32;
+    const int n = B.n;
+    if (jobs.n_dw + n > tc::kBwdMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 backward: too many layers");
+    add(B.tmDL128, B.tmAct128[n - 1], nullptr, 256, B.L[n - 1].k_out, B.L[n - 1].k_in, F.ld_in[n - 1], 1, F.gWp[n - 1], F.gbp[n - 1]);
+    for (int l = n - 2; l >= 0; --l) {
+      // dY[l] is the output of chain unit n-2-l
+      const uint32_t* ready = S->ready + (size_t)(ci * tc::kChUnits + (n - 2 - l)) * n_tiles;
+      if (l == 0 && B.col_off0 > 0)
+        // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to the scratch that the tail launch
+        // (k_unpack_table modes 1 / 2) turns into dW0 / db0
+        add(B.tmDY128[0], B.tmAct128[0], ready, 128, B.L[0].k_out, 64, 64, 0, B.dW0x, F.gbp[0]);
+      else
+        add(B.tmDY128[l], B.tmAct128[l], ready, l == 0 ? 128 : 256, B.L[l].k_out, B.L[l].k_in, F.ld_in[l], 1, F.gWp[l], F.gbp[l]);
+      // (dY[0] of a chain whose input gradient is needed is read again by the warp-gradient GEMM: kept)
+      if (discard && !(l == 0 && B.need_dx0)) {
+        jobs.dw[jobs.n_dw - 1].dy_base = reinterpret_cast<unsigned char*>(B.dY[l]);
+        jobs.dw[jobs.n_dw - 1].dy_pitch = B.L[l].np * 2;
+      }
+    }
+  }
+  // chain pairs : dW pairs.  Measured on the B200 (profiles/r02_bwd_experiments.md): both roles run ~25 % slower side by side than
+  // alone (they share L2 / HBM), a dW pair is bound by its operand loads (~0.85 us per 128-row stage whatever the job), and the
+  // launch is fastest when the two roles finish together: 36 : 38 with two networks (10 jobs), 39 : 35 with one (5 jobs).
+  // MARF_BWD_CHAIN_CLUSTERS overrides.
+  double wsum = 0;
+  for (int i = 0; i < jobs.n_dw; ++i) wsum += weight[i];
+  int n_chain = (int)(total_pairs * (n_chains == 2 ? 0.49 : 0.53) + 0.5);
+  if (const char* e = getenv("MARF_BWD_CHAIN_CLUSTERS")) n_chain = atoi(e);
+  const int n_items = (n_tiles + 3) / 4 * n_chains;
+  n_chain = std::max(1, std::min(n_chain, std::min(n_items, total_pairs - jobs.n_dw)));
+  if (n_chains == 2 && n_chain > 1) n_chain &= ~1;            // an even count keeps every chain pair on one network
+  const int n_dw_pairs = total_pairs - n_chain;
+  if (n_dw_pairs < jobs.n_dw) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 backward: fewer CTA pairs than dW jobs");
+  // pairs per job: proportional to the weights, largest-remainder rounding, at least one each
+  int cnt[tc::kBwdMaxJobs], used = 0;
+  double rem[tc::kBwdMaxJobs];
+  for (int i = 0; i < jobs.n_dw; ++i) {
+    const double x = n_dw_pairs * weight[i] / wsum;
+    cnt[i] = std::max(1, (int)x);
+    rem[i] = x - cnt[i];
+    used += cnt[i];
+  }
+  while (used < n_dw_pairs) {
+    int best = 0;
+    for (int i = 1; i < jobs.n_dw; ++i) if (rem[i] > rem[best]) best = i;
+    cnt[best]++; rem[best] -= 1.0; used++;
+  }
+  while (used > n_dw_pairs) {                                 // (the minimum of one pair per job overshot)
+    int best = -1;
+    for (int i = 0; i < jobs.n_dw; ++i) if (cnt[i] > 1 && (best < 0 || rem[i] < rem[best])) best = i;
+    if (best < 0) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 backward: cannot place the dW jobs");
+    cnt[best]--; rem[best] += 1.0; used--;
+  }
+  int begin = 0;
+  for (int i = 0; i < jobs.n_dw; ++i) { jobs.dw[i].pair_begin = begin; jobs.dw[i].pair_count = cnt[i]; begin += cnt[i]; }
+  jobs.n_chain_clusters = n_chain;
+  jobs.prefetch_ahead = getenv("MARF_BWD_PREFETCH") ? atoi(getenv("MARF_BWD_PREFETCH")) : 0;
+  const int grid = 2 * (n_chain + n_dw_pairs);
+  // timing experiments (results invalid): MARF_BWD_DBG bit 1 = the dW pairs do not wait for the chain pairs, bit 2 = the chain
+  // pairs do not publish their tiles
+  const int dbg = getenv("MARF_BWD_DBG") ? atoi(getenv("MARF_BWD_DBG")) : 0;
+  if (dbg & 1) for (int i = 0; i < jobs.n_dw; ++i) jobs.dw[i].ready = nullptr;
+  if (dbg & 2) jobs.chain.ready = nullptr;
+  // diagnostics (MARF_BWD_TRACE=<n>): begin / end time of every CTA pair of the n-th launch
+  static int calls = 0;
+  const char* te = getenv("MARF_BWD_TRACE");
+  const bool tracing = te && ++calls == atoi(te);
+  if (tracing) {
+    cudaMalloc(&jobs.trace, (size_t)grid * sizeof(unsigned long long));
+    cudaMemset(jobs.trace, 0, (size_t)grid * sizeof(unsigned long long));
+  }
+  launch_k_cluster(tc::k_tc_bwd, grid, tc::kChThreads, tc::kChSmem + 1024, st, 2, jobs);
+  BF_LAUNCH(h);
+  if (tracing) {
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> tr(grid);
+    cudaMemcpy(tr.data(), jobs.trace, tr.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(jobs.trace);
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid / 2; ++c) t0 = std::min(t0, tr[2 * c]);
+    double c_end = 0, d_end = 0;
+    for (int c = 0; c < grid / 2; ++c) (c < n_chain ? c_end : d_end) = std::max(c < n_chain ? c_end : d_end, (tr[2 * c + 1] - t0) * 1e-3);
+    fprintf(stderr, "k_tc_bwd trace: %d chain pairs (last ends %.1f us), %d dW pairs (last ends %.1f us), rows %d; per pair begin/end in us\n",
+            n_chain, c_end, n_dw_pairs, d_end, rows);
+    for (int c = 0; c < grid / 2; ++c) {
+      int job = -1;
+      if (c >= n_chain) for (int i = 0; i < jobs.n_dw; ++i) if (c - n_chain >= jobs.dw[i].pair_begin) job = i;
+      fprintf(stderr, "  pair %2d %s job %2d  %8.1f %8.1f\n", c, c < n_chain ? "chain" : "dW   ", job, (tr[2 * c] - t0) * 1e-3, (tr[2 * c + 1] - t0) * 1e-3);
+    }
+  }
+  return MARF_OK;
+}
+
 static int thin_fwd(marf_handle* h, cudaStream_t st, BfChain& B, int rows, const float* W, const float* bias) {
   int l = B.n - 1;
   int width = B.L[l].k_in, out = B.L[l].k_out;
@@ -1336,6 +1485,11 @@ static int bf_backward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_
   int rc = MARF_OK;
   if (S->img.fused && (!implicit || S->msk.fused)) {
     BfChain* both[2] = {&S->img, &S->msk};
+    if (bwd_fused_enabled() && S->num_sms >= 2 * (2 + 2 * tc::kBwdMaxJobs)) {
+      rc = launch_bwd(h, st, both, implicit ? 2 : 1, rg.padded);          // dX chains + every dW / db GEMM, one launch
+      if (rc) return rc;
+      return launch_dx0(h, st, c_img, 1, rg.padded, rg);                  // dX0 + encoding backward -> per-patch G
+    }
     rc = launch_chain(h, st, both, implicit ? 2 : 1, rg.padded, false);   // dlogits -> dY[n-2] -> ... -> dY[0], one launch
     if (rc) return rc;
     rc = launch_dx0(h, st, c_img, 1, rg.padded, rg);                      // dX0 + encoding backward -> per-patch G

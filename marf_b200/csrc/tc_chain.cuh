@@ -57,7 +57,16 @@ struct ChainJobs {
   int n_tiles;            // 128-row tiles per chain
   int dbg;                // timing experiments only (results invalid): 1 no TMA stores, 2 weights loaded once per CTA, 4 no epilogue math
   long long* trace;       // diagnostics: clock64() stamps of CTA 0, [item < 2][unit][half][16]; nullptr in production
+  // CH_DX inside k_tc_bwd (tc_bwd.cuh): the dW pairs of the same launch consume every unit's output tile by tile.
+  uint32_t* ready;        // [chain][unit][n_tiles]: set to `epoch` (release, gpu scope) once the tile's TMA stores have completed
+  uint32_t epoch;         // launch counter of the handle (flags are never reset)
+  int store_last;         // dY tiles are stored with L2 evict_last priority (they are consumed out of L2 by the same launch)
+  int interleave;         // work item -> (chain = item % n, tile group = item / n) instead of chain-major order
 };
+
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d));
@@ -83,9 +92,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 // epilogue warps of both CTAs arrive on the leader's epi_done barriers.  Per tile-layer this takes a quarter of the SMEM
 // bandwidth off the MMA operand reads and halves the weight stream.
 template <int MODE, int CL>
-__global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constant__ ChainJobs jobs) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__device__ __forceinline__ void chain_role(const ChainJobs& jobs, uint8_t* smem, const int cid, const int ncl) {
   constexpr bool kOut = MODE == CH_FWD;          // the forward chain ends with the thin output layer
   const uint32_t s_act = smem_u32(smem + kChActOff);
   const uint32_t s_w = smem_u32(smem + kChWOff);
@@ -105,10 +112,13 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CL == 2 ? cluster_ctarank() : 0u;
-  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;      // work is distributed over clusters
+  // work is distributed over clusters: cluster `cid` of `ncl` takes the items cid, cid + ncl, ...
   constexpr int kGroup = 2 * CL;                                        // tiles per work item
   const int n_pairs = (jobs.n_tiles + kGroup - 1) / kGroup;             // work items per chain
   const int n_items = n_pairs * jobs.n;
+  const bool ilv = jobs.interleave != 0;
+  auto chain_of = [&](int item) -> int { return ilv ? item % jobs.n : item / n_pairs; };
+  auto group_of = [&](int item) -> int { return ilv ? item / jobs.n : item % n_pairs; };
 
   if (threadIdx.x == 0) {
     for (int c = 0; c < jobs.n; ++c) {
@@ -154,8 +164,8 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
         ++wit;
       };
       auto load_in = [&](int item) {
-        const ChainJob& J = jobs.c[item / n_pairs];
-        const int g0 = kGroup * (item % n_pairs);                       // first tile of the work item
+        const ChainJob& J = jobs.c[chain_of(item)];
+        const int g0 = kGroup * group_of(item);                         // first tile of the work item
         const int tile0 = g0 + 2 * (int)rank;                           // this CTA's two tiles
         const int n_valid = min(kGroup, jobs.n_tiles - g0);
         mbar_wait(in_empty, (n_in & 1) ^ 1);
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       };
       if (cid < n_items) load_in(cid);
       for (int item = cid; item < n_items; item += ncl) {
-        const ChainJob& J = jobs.c[item / n_pairs];
+        const ChainJob& J = jobs.c[chain_of(item)];
         load_w(&J.u[0].tmW, 0, 0);
         load_w(&J.u[0].tmW, 0, 1);
         for (int u = 1; u < kChUnits; ++u) {
@@ -243,7 +253,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
       bool first_item = true;
       int it_no = 0;
       auto stamp = [&](int u, int h, int e) {
-        if (jobs.trace && blockIdx.x == 0 && it_no < 2 && mi == 0) {
+        if (jobs.trace && cid == 0 && rank == 0 && it_no < 2 && mi == 0) {
           jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + e] = clock64();
           if (e == 1) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 3] = jobs.trace[0] + w_wait;   // cumulative wait on weight chunks
         }
@@ -319,14 +329,16 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
     uint32_t c_acc0 = 0, c_acc1 = 0, c_free = 0;
     int it_no = 0;
+    uint32_t* pend_flag = nullptr;       // (group leader) flag of the newest stored tile that is not published yet
     const uint32_t epi_bar0 = CL == 2 ? mapa_u32(smem_u32(&epi_done[0]), 0) : 0u;     // the leader CTA's epi_done[0]
     for (int item = cid; item < n_items; item += ncl, ++it_no) {
-      const bool tr = jobs.trace && blockIdx.x == 0 && it_no < 2 && (threadIdx.x == 64 || threadIdx.x == 192);
+      const bool tr = jobs.trace && cid == 0 && rank == 0 && it_no < 2 && (threadIdx.x == 64 || threadIdx.x == 192);
       auto stamp = [&](int u, int h, int e) {
         if (tr) jobs.trace[((it_no * 4 + u) * 2 + h) * 16 + 4 + grp * 6 + e] = clock64();
       };
-      const ChainJob& J = jobs.c[item / n_pairs];
-      const int tile = kGroup * (item % n_pairs) + 2 * (int)rank + grp;
+      const int chain = chain_of(item);
+      const ChainJob& J = jobs.c[chain];
+      const int tile = kGroup * group_of(item) + 2 * (int)rank + grp;
       const bool valid = tile < jobs.n_tiles;
       const size_t grow = (size_t)tile * kTileM + r;
       for (int u = 0; u < kChUnits; ++u) {
@@ -363,7 +375,7 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
               const uint32_t ob = s_act + (uint32_t)(grp * 4 + j) * kChSlab + sw_row;
               uint32_t obits[2] = {0u, 0u};
               const uint32_t mw[2] = {jj == 0 ? mb.x : mb.z, jj == 0 ? mb.y : mb.w};
-              const uint32_t bp = smem_u32(smem + kChBiasOff) + (uint32_t)(((item / n_pairs) * kChUnits + u) * 256 + j * 64) * 4;
+              const uint32_t bp = smem_u32(smem + kChBiasOff) + (uint32_t)((chain * kChUnits + u) * 256 + j * 64) * 4;
               tmem_ld_wait();
               stamp(u, h, 2 + jj);
 #pragma unroll
@@ -411,10 +423,20 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
               // forward activations are next read by the dW pass, a whole backward pass later: evict first.  The dY of the dX
               // chain are read by the dX0 GEMM and the dW launch right after this kernel: normal priority, so that what the L2
               // still holds of them at the end of the kernel is served from there.
-              const uint64_t pol = MODE == CH_FWD ? kEvictFirst : kEvictNormal;
+              const uint64_t pol = MODE == CH_FWD ? kEvictFirst : (jobs.store_last ? kEvictLast : kEvictNormal);
               tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, pol);
               tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, pol);
               bulk_commit();
+              if (MODE == CH_DX && jobs.ready && h == 1) {
+                // lagged hand-over to the dW pairs: everything older than this unit's two store groups has completed, i.e.
+                // the tile this group stored one unit ago (a TMA store needs ~3k cycles; waiting for the newest would stall)
+                if (pend_flag) {
+                  bulk_wait<2>();
+                  fence_proxy_async_all();
+                  st_release_gpu(pend_flag, jobs.epoch);
+                }
+                pend_flag = jobs.ready + ((size_t)(chain * kChUnits + u) * jobs.n_tiles + tile);
+              }
             }
           }
           stamp(u, h, 5);
@@ -441,7 +463,13 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
         }
       }
     }
-    if (gleader) bulk_wait<0>();
+    if (gleader) {
+      bulk_wait<0>();
+      if (MODE == CH_DX && pend_flag) {
+        fence_proxy_async_all();
+        st_release_gpu(pend_flag, jobs.epoch);
+      }
+    }
   }
   tc_fence_before();
   if (CL == 2) cluster_sync_all();        // the peer may still signal this CTA's barriers / read its SMEM until here
@@ -450,6 +478,13 @@ __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constan
     tc_fence_after();
     if (CL == 2) tmem_dealloc_2sm(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int MODE, int CL>
+__global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constant__ ChainJobs jobs) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  chain_role<MODE, CL>(jobs, smem, (int)blockIdx.x / CL, (int)gridDim.x / CL);
 }
 
 }  // namespace tc

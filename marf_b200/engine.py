@@ -108,7 +108,7 @@ class PlanarEngine:
     def workspace_bytes(self) -> int:
         return int(self.lib.marf_workspace_bytes(self.handle))
 
-    PROF_CLASSES = ("k_tc_chain<fwd>", "k_tc_chain<dx>", "k_tc_dw", "(unused)", "k_tc_gemm<64,warp_grad>")
+    PROF_CLASSES = ("k_tc_chain<fwd>", "k_tc_chain<dx>", "k_tc_dw", "k_tc_bwd", "k_tc_gemm<64,warp_grad>")
 
     def profile(self, enable: bool):
         """Event pairs around the tensor-core launches of the bf16 path (marf_profile); see profile_read."""

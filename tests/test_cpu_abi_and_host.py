@@ -171,31 +171,36 @@ def test_no_predicated_tensor_core_mma_in_sass():
 
 
 def test_bench_roofline_arithmetic():
-    """bench.roofline_lines: algorithmic bytes / FLOP per kernel class, the choice of the dominant kernel and its bound."""
-    import argparse
+    """bench.roofline_lines: algorithmic FLOP / bytes per kernel class, the dominant kernel against the TENSOR roofline
+     with the HBM view and the traffic ratio beside it."""
     import bench
     wl = bench.workload("config2", 1)
     pk = dict(bf16_burst=1600.0, bf16_sustained=1400.0, hbm=6500.0, source="test")
-    kern = {"k_tc_dw": dict(us_per_launch=320.0, launches_per_step=1.0),
+    kern = {"k_tc_bwd": dict(us_per_launch=400.0, launches_per_step=1.0),
             "k_tc_chain<fwd>": dict(us_per_launch=220.0, launches_per_step=1.0),
-            "k_tc_chain<dx>": dict(us_per_launch=195.0, launches_per_step=1.0),
             "k_tc_gemm<64,warp_grad>": dict(us_per_launch=38.0, launches_per_step=1.0)}
-    args = argparse.Namespace(gpus=1, workload="config2", precision="bf16")
-    out = bench.roofline_lines(wl, kern, pk, 216000, 650.0, args)
+    out = bench.roofline_lines(wl, "config2", "bf16", kern, pk, 216000, 650.0, 1)
     rows = 216064                                        # 216000 padded to 128
     r = out["roofline"]
-    assert r["kernel"] == "k_tc_dw" and r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == 6500.0
-    # two networks: 3 x (512 + 512) + (512 + 16) + (512 + 128) bytes per pixel-sample row each
-    assert abs(r["achieved"] - 2 * (3 * 1024 + 528 + 640) * rows / 320e-6 / 1e9) < 1e-6
-    assert abs(r["frac"] - r["achieved"] / 6500.0) < 1e-12
+    assert r["kernel"] == "k_tc_bwd" and r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] == 1600.0
+    # algorithmic FLOP of the three kernel classes add up to SURVEY 8a's 2,853,888 per pixel-sample (image MLP + mask head)
+    flop, byt = bench.kernel_tables(wl)
+    assert flop["k_tc_chain<fwd>"] + flop["k_tc_bwd"] + flop["k_tc_gemm<64,warp_grad>"] == 2_853_888
+    assert flop["k_tc_bwd"] == flop["k_tc_dw"] + flop["k_tc_chain<dx>"]
+    flop1, _ = bench.kernel_tables(bench.workload("config4", 1))
+    assert flop1["k_tc_chain<fwd>"] + flop1["k_tc_bwd"] + flop1["k_tc_gemm<64,warp_grad>"] == 1_236_480
+    assert abs(r["achieved"] - flop["k_tc_bwd"] * rows / 400e-6 / 1e12) < 1e-9
+    assert abs(r["frac"] - r["achieved"] / 1600.0) < 1e-12 and abs(r["frac_of_sustained"] - r["achieved"] / 1400.0) < 1e-12
+    # two networks: every X_l once (4 x 512 + 128 B), dlogits tiles, mask bits; dY_0 of the image chain out
+    assert r["algorithmic_bytes"] == (2 * (4 * 512 + 128 + 32 + 4 * 32) + 512) * rows
+    assert abs(r["hbm_view"]["achieved"] - r["algorithmic_bytes"] / 400e-6 / 1e9) < 1e-6
     by = {k["kernel"]: k for k in out["kernels"]}
-    assert [k["kernel"] for k in out["kernels"]][0] == "k_tc_dw"          # sorted by time in the step
+    assert [k["kernel"] for k in out["kernels"]][0] == "k_tc_bwd"          # sorted by time in the step
     fwd = by["k_tc_chain<fwd>"]
-    assert abs(fwd["hbm_gbs"] - 2 * (128 + 4 * 512 + 4 * 32 + 16) * rows / 220e-6 / 1e9) < 1e-6
-    assert abs(fwd["tensor_tflops"] - 2 * 2 * (64 * 256 + 3 * 256 * 256 + 256 * 2) * rows / 220e-6 / 1e12) < 1e-9
-    assert out["step_roofline"]["frac"] == 650.0 / 1400.0
-    # traffic comes from profiles/r01_kernel_traffic.json when it holds this workload
-    assert r["traffic"] is None or r["traffic"] > 1e9
+    assert abs(fwd["hbm_view"]["achieved"] - 2 * (128 + 4 * 512 + 4 * 32 + 16) * rows / 220e-6 / 1e9) < 1e-6
+    assert out["step_roofline"]["frac"] == 650.0 / 1600.0 and out["step_roofline"]["frac_of_sustained"] == 650.0 / 1400.0
+    # traffic comes from the committed ncu capture when it holds this workload
+    assert r["traffic"] is None or r["traffic"] > 1e8
     # fp32 / no per-kernel pass: falls back to the whole-step figure
-    out2 = bench.roofline_lines(wl, {}, pk, 216000, 650.0, args)
+    out2 = bench.roofline_lines(wl, "config2", "bf16", {}, pk, 216000, 650.0, 1)
     assert out2["roofline"]["bound"] == "tensor" and out2["roofline"]["traffic"] is None

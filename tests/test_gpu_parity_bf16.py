@@ -166,6 +166,7 @@ def test_step_is_graph_capturable(name):
         t.fill_(7.0)
     graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(kw["g_warp"].cpu(), ref["grads"]["gwarp"])
-    assert torch.equal(kw["g_mlp_w"][1].cpu(), ref["grads"]["gW1"])
+    # (the weight gradients are summed with fp32 reductions whose order varies from run to run: equal to reduction order)
+    for got, want in ((kw["g_warp"].cpu(), ref["grads"]["gwarp"]), (kw["g_mlp_w"][1].cpu(), ref["grads"]["gW1"])):
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
     eng.close()

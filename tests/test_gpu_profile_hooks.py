@@ -20,10 +20,11 @@ def test_profile_records_every_tensor_core_launch():
         gpu_util.run_step(eng, cfg, params, images, it, progress)
     rec = eng.profile_read()
     eng.profile(False)
-    for k in ("k_tc_chain<fwd>", "k_tc_chain<dx>", "k_tc_dw", "k_tc_gemm<64,warp_grad>"):
+    for k in ("k_tc_chain<fwd>", "k_tc_bwd", "k_tc_gemm<64,warp_grad>"):      # (k_tc_bwd = the dX chains + every dW GEMM, one launch)
         ms, n = rec[k]
         assert n == 3, (k, n)
         assert 0.0 < ms < 50.0, (k, ms)
+    assert rec["k_tc_dw"][1] == 0 and rec["k_tc_chain<dx>"][1] == 0
     assert all(n == 0 for _, n in eng.profile_read().values())           # read clears
     gpu_util.run_step(eng, cfg, params, images, it, progress)
     assert all(n == 0 for _, n in eng.profile_read().values())           # disabled: nothing recorded
