@@ -19,7 +19,7 @@ def _engine_for(device):
 
 def _to_tensor(im):
     """PIL image -> float32 [C,h,w] in [0,1] (what torchvision's to_tensor does for 8-bit images)."""
-    a = np.asarray(im)
+    a = np.array(im)
     if a.ndim == 2:
         a = a[:, :, None]
     return torch.from_numpy(np.ascontiguousarray(a.transpose(2, 0, 1))).float().div(255)

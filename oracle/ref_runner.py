@@ -70,8 +70,22 @@ def _install_stubs():
             PIL.Image.fromarray(np.asarray(arr)).save(path)
         mod("imageio", imsave=imsave)
     if "kornia" not in sys.modules:
-        def normalize_homography(*a, **k):
-            raise NotImplementedError("kornia stub: run the reference with --use_homographies!")
+        def normalize_homography(dst_pix_trans_src_pix, dsize_src, dsize_dst):
+            """kornia.geometry.conversions.normalize_homography restated from kornia's documentation (kornia is unpinned in
+            the reference's requirements.yaml:27 and absent here): N_dst . H . N_src^-1 with
+            N(h, w) = [[2/(w-1), 0, -1], [0, 2/(h-1), -1], [0, 0, 1]] (normal_transform_pixel, eps 1e-14 for size-1 axes)."""
+            import torch
+
+            def normal_transform_pixel(height, width, like):
+                n = torch.tensor([[1.0, 0.0, -1.0], [0.0, 1.0, -1.0], [0.0, 0.0, 1.0]], dtype=like.dtype, device=like.device)
+                n[0, 0] = n[0, 0] * 2.0 / (width - 1 if width != 1 else 1e-14)
+                n[1, 1] = n[1, 1] * 2.0 / (height - 1 if height != 1 else 1e-14)
+                return n.unsqueeze(0)
+            src_h, src_w = dsize_src
+            dst_h, dst_w = dsize_dst
+            src_norm = normal_transform_pixel(src_h, src_w, dst_pix_trans_src_pix)
+            dst_norm = normal_transform_pixel(dst_h, dst_w, dst_pix_trans_src_pix)
+            return dst_norm @ (dst_pix_trans_src_pix @ torch.linalg.inv(src_norm))
         conv = mod("kornia.geometry.conversions", normalize_homography=normalize_homography)
         geo = mod("kornia.geometry", conversions=conv)
         mod("kornia", geometry=geo)
