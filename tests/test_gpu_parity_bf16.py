@@ -1,6 +1,13 @@
 """GPU parity (precision=bf16, the tcgen05 tensor-core mode): bf16 operands / fp32 accumulate vs the fp32 oracle.
-Tolerances are stated separately from the fp32 mode (north_star): outputs <= 2e-2 max-abs (observed ~5e-3),
-losses 2e-2 relative, gradients 5e-2 relative L2 per tensor."""
+Tolerances are stated separately from the fp32 mode (north_star), per quantity, 2-3x the largest error observed over
+BF16_CASES (single-call, two-phase and chunked runs):
+  outputs (rgb, mask)      6e-3 max-abs      (observed <= 2.5e-3)
+  losses                   2e-3 relative     (observed <= 2.0e-4)
+  weight / bias gradients  5e-2 relative L2  (observed <= 2.3e-2)
+  warp gradient            1.5e-1 relative L2 (observed 1.4e-2 ... 1.06e-1): a small residual of per-pixel terms that cancel; its
+                           error is set by the bf16 rounding of the FORWARD pass (the 2.5e-3 error of the prediction against
+                           residuals p - t of ~0.05), not by the backward GEMMs — profiles/r02_bf16_error_budget.txt.  What it
+                           means for the product: profiles/r02_endpoint_parity.txt (bf16 registers to within 0.006 px of fp32)."""
 import numpy as np
 import pytest
 import torch
@@ -10,11 +17,13 @@ import planar_oracle as po
 
 pytestmark = pytest.mark.gpu
 
-OUT_TOL = 2e-2
-LOSS_RTOL = 2e-2
-GRAD_L2 = 1.5e-1
+OUT_TOL = 6e-3
+LOSS_RTOL = 2e-3
+GRAD_L2 = 5e-2
+GWARP_L2 = 1.5e-1
 
 BF16_CASES = ["mid_mask", "mid_mask_c2f", "mid_nomask_edges", "implicit", "implicit_edges",
+              "implicit_edges_b5",               # (BASELINE config 2's real shape: 5 patches 180x240, learned mask + edge term)
               "wide512_L10", "wide512_c2f"]      # (BASELINE config 5's network: 4x512, posenc L=10, per-layer tensor-core kernels)
 
 
@@ -47,7 +56,7 @@ def _check(res, cfg, params, images, it, progress, label=""):
     for k, v in named.items():
         rel = ((res["grads"][k].double() - v.double()).norm() / (v.double().norm() + 1e-30)).item()
         report[k] = rel
-        assert rel <= GRAD_L2, (k, report)
+        assert rel <= (GWARP_L2 if k == "gwarp" else GRAD_L2), (k, report)
     print(label, {k: f"{v:.2e}" for k, v in report.items()})
     assert res["nonfinite"] == 0.0
 

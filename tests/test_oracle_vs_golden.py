@@ -103,6 +103,9 @@ def test_step(name):
 @pytest.mark.parametrize("name,over", [
     ("train_small_c2f", dict(cases.SMALL, use_masks=True, barf_c2f=(0.0, 0.4), max_iter=40)),
     ("train_small_edges", dict(cases.SMALL, use_masks=True, use_edges=True, max_iter=40)),
+    # the default 4x256 / L=8 network (the shape the bf16 tensor-core path serves): MID size, and the learned mask at full size
+    ("train_mid256_c2f", dict(cases.MID, use_masks=True, barf_c2f=(0.0, 0.4), max_iter=40)),
+    ("train_mid256_implicit", dict(batch_size=2, use_masks=True, use_implicit_mask=True, use_edges=True, max_iter=40)),
 ])
 def test_training_trajectory(name, over):
     """Model.train_iteration + loop tail (model/planar.py:154-158,187-209): seed-matched init, Adam,
@@ -116,6 +119,11 @@ def test_training_trajectory(name, over):
     images = cases.make_images(cfg, seed=43)
     hist = po.adam_train(params, images, cfg, n_iter=cfg.max_iter)
     for k in ("render", "rgb", "mask", "edge", "all"):
-        np.testing.assert_allclose([h[k] for h in hist], g["hist_" + k], rtol=2e-4, atol=1e-8, err_msg=k)
-    np.testing.assert_allclose(params.warp.detach().numpy(), g["warp_final"], rtol=0, atol=2e-5)
+        # (256-wide: 40 Adam steps amplify the fp32 summation-order differences between this run's BLAS threading and the golden run's)
+        np.testing.assert_allclose([h[k] for h in hist], g["hist_" + k], rtol=2e-4 if "small" in name else 1e-3,
+                                   atol=1e-8 if "small" in name else 1e-5, err_msg=k)
+    # (Adam moves a parameter by ~lr = 1e-3 per step whatever the gradient's size: where a warp-gradient entry is near zero its
+    #  rounding decides the direction of a step, so the full-posenc 256-wide run pins the warps to about one step)
+    np.testing.assert_allclose(params.warp.detach().numpy(), g["warp_final"], rtol=0,
+                               atol=2e-5 if "small" in name else (1e-4 if "c2f" in name else 1.5e-3))
     assert float(np.abs(g["warp_final"][0]).max()) == 0.0
