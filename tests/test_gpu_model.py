@@ -108,18 +108,20 @@ def test_train_iteration_256_wide_matches_reference_trajectory(tmp_path, name, p
         loss = m.train_iteration(var, _Loader())
         for k in hist:
             hist[k].append(float(loss[k]))
-    # (warps: Adam moves a parameter by ~lr = 1e-3 per step whatever the gradient's size; near-zero gradient entries make the
-    #  full-posenc run reproducible to about one or two steps only — the oracle itself is 6e-4 from the reference there)
-    rtol, wtol = (1e-2, 2e-3) if precision == "bf16" else (5e-3, 3e-4)
-    if implicit:
-        wtol = 3e-3
+    rtol = 1e-2 if precision == "bf16" else 5e-3
     for k in hist:
         # the first ten iterations tightly; then the trajectory amplifies summation-order differences (Adam normalises every
         # gradient entry, so the rounding of near-zero entries steers whole steps): observed up to 1.2 % (fp32) / 2.4 % (bf16) by
         # iteration 40, growing smoothly from 1e-6 — a wrong gradient would show in the first iterations
         np.testing.assert_allclose(hist[k][:10], g["hist_" + k][:10], rtol=rtol, atol=2e-5, err_msg=k + " (first 10)")
         np.testing.assert_allclose(hist[k], g["hist_" + k], rtol=6 * rtol, atol=1e-4, err_msg=k)
-    np.testing.assert_allclose(m.graph.warp_param.weight.detach().cpu().numpy(), g["warp_final"], rtol=0, atol=wtol)
+    # Final warps: Adam moves an entry by ~lr = 1e-3 per step whatever its gradient's size, so an entry whose gradient sits at
+    # the rounding level random-walks (observed run to run: up to 2.5e-3 in fp32, 4.7e-3 with the learned mask, of |h| ~ 0.05
+    # after 40 steps; the CPU oracle itself ends 6e-4 from the reference there).  A wrong gradient sign would move an entry by
+    # 40 x 1e-3: bound 8e-3 per entry, 8 % in relative L2.
+    w, wg = m.graph.warp_param.weight.detach().cpu().double().numpy(), g["warp_final"].astype(np.float64)
+    assert np.abs(w - wg).max() <= 8e-3, np.abs(w - wg).max()
+    assert np.linalg.norm(w - wg) <= 8e-2 * np.linalg.norm(wg), (np.linalg.norm(w - wg), np.linalg.norm(wg))
     m.check_finite()
 
 
@@ -184,9 +186,14 @@ def test_checkpoint_resume_continues_the_run(tmp_path, fused):
     assert b.load_checkpoint(path, resume=True) == 4 and b.graph.it == a.graph.it - 4
     run(b, var_b, 4)
     assert b.it == a.it == 8
+    # Adam moves an entry by ~lr = 1e-3 per step whatever its gradient's size, and the fp32 step sums with atomics whose order
+    # changes from run to run: an entry whose gradient is ~0 may step the other way in the second run.  Hence a relative-L2
+    # bound per tensor (a lost moment buffer or a wrong iteration counter moves EVERY entry by ~1e-3 per step: rel-L2 ~ 1e-1)
+    # plus a max-abs bound of two steps for the isolated entries.
     for (k, pa), (_, pb) in zip(a.graph.state_dict().items(), b.graph.state_dict().items()):
-        err = (pa.double() - pb.double()).abs().max().item()
-        assert err <= 1e-4 * (pa.double().abs().max().item() + 1e-6) + 1e-6, (k, err)
+        d = pa.double() - pb.double()
+        assert d.norm().item() <= 2e-3 * (pa.double().norm().item() + 1e-6) + 1e-6, (k, d.norm().item(), pa.double().norm().item())
+        assert d.abs().max().item() <= 2.5e-3, (k, d.abs().max().item())
     # parameters only
     c, _ = make()
     assert c.load_checkpoint(path, resume=False) == 0 and c.it == 0
