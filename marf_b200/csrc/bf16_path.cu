@@ -626,7 +626,10 @@ static int set_tc_attrs(marf_handle* h) {
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_bwd<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_bwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_FWD, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  BF_TRY(h, cudaFuncSetAttribute(tc::k_tc_chain<tc::CH_DX, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (3 * 512 + 3) * 4));
   BF_TRY(h, cudaFuncSetAttribute(k_thin_dw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * (1 * 512 + 1) * 4));
   return MARF_OK;
@@ -1003,6 +1006,12 @@ static int launch_dw_all(marf_handle* h, cudaStream_t st, BfChain** chains, int 
   return MARF_OK;
 }
 
+// schedule of the chain kernels on CTA pairs: 1 = tile-staggered N = 256 (tc_chain.cuh: chain_role_staggered), 0 = two halves in lockstep
+static int chain_sched() {
+  static const int v = getenv("MARF_CHAIN_SCHED") ? atoi(getenv("MARF_CHAIN_SCHED")) : 0;
+  return v;
+}
+
 // ---- fused chains (tc_chain.cuh): all hidden layers (+ output layer) of up to two MLPs in ONE launch
 static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n_chains, int rows, bool forward) {
   Bf16State* S = h->bf16;
@@ -1010,6 +1019,7 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
   // CTA pairs (cluster of 2, cta_group::2 MMAs) by default; MARF_CHAIN_CL=1 selects the single-CTA variant (tests, A/B runs)
   const char* cl_env = getenv("MARF_CHAIN_CL");
   const int cl = (cl_env && atoi(cl_env) == 1) || S->num_sms < 2 ? 1 : 2;
+  const bool stag = cl == 2 && chain_sched() == 1;          // (weight chunks: this CTA's 128 of 256 rows -> the 128-row boxes)
   tc::ChainJobs jobs{};
   jobs.n = n_chains;
   jobs.n_tiles = rows / 128;
@@ -1023,7 +1033,7 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
       J.tmIn = B.tmAct128[0];
       J.tmWout = cl == 2 ? B.tmWout8 : B.tmWout16;
       for (int u = 0; u < tc::kChUnits; ++u) {
-        J.u[u].tmW = cl == 2 ? B.L[u].tmWk64 : B.L[u].tmWk128;
+        J.u[u].tmW = (cl == 2 && !stag) ? B.L[u].tmWk64 : B.L[u].tmWk128;
         J.u[u].tmOut = B.tmAct128[u + 1];
         J.u[u].bias = (u == 0 && B.col_off0 > 0) ? B.zero_bias : B.f32->bp[u];   // (class-table mode: b0 lives in Wk)
         J.u[u].bits = B.bits[u + 1];
@@ -1037,7 +1047,7 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
       J.tmWout = B.tmWout16;                 // unused
       for (int u = 0; u < tc::kChUnits; ++u) {
         const int l = n - 1 - u;
-        J.u[u].tmW = u == 0 ? (cl == 2 ? B.tmWlast64 : B.tmWlast128) : (cl == 2 ? B.L[l].tmWt64 : B.L[l].tmWt128);
+        J.u[u].tmW = u == 0 ? ((cl == 2 && !stag) ? B.tmWlast64 : B.tmWlast128) : ((cl == 2 && !stag) ? B.L[l].tmWt64 : B.L[l].tmWt128);
         J.u[u].tmOut = B.tmDY128[l - 1];
         J.u[u].bias = nullptr;
         J.u[u].bits = B.bits[l];
@@ -1056,7 +1066,10 @@ static int launch_chain(marf_handle* h, cudaStream_t st, BfChain** chains, int n
     cudaMalloc(&jobs.trace, 2 * 4 * 2 * 16 * sizeof(long long));
     cudaMemset(jobs.trace, 0, 2 * 4 * 2 * 16 * sizeof(long long));
   }
-  if (cl == 2) {
+  if (stag) {
+    if (forward) launch_k_cluster(tc::k_tc_chain<tc::CH_FWD, 2, 1>, grid, tc::kChThreads, smem, st, 2, jobs);
+    else launch_k_cluster(tc::k_tc_chain<tc::CH_DX, 2, 1>, grid, tc::kChThreads, smem, st, 2, jobs);
+  } else if (cl == 2) {
     if (forward) launch_k_cluster(tc::k_tc_chain<tc::CH_FWD, 2>, grid, tc::kChThreads, smem, st, 2, jobs);
     else launch_k_cluster(tc::k_tc_chain<tc::CH_DX, 2>, grid, tc::kChThreads, smem, st, 2, jobs);
   } else {
@@ -1113,7 +1126,7 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
     J.tmWout = B.tmWout16;                   // unused
     for (int u = 0; u < tc::kChUnits; ++u) {
       const int l = n - 1 - u;
-      J.u[u].tmW = u == 0 ? B.tmWlast64 : B.L[l].tmWt64;
+      J.u[u].tmW = chain_sched() == 1 ? (u == 0 ? B.tmWlast128 : B.L[l].tmWt128) : (u == 0 ? B.tmWlast64 : B.L[l].tmWt64);
       J.u[u].tmOut = B.tmDY128[l - 1];
       J.u[u].bias = nullptr;
       J.u[u].bits = B.bits[l];
@@ -1202,7 +1215,8 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
     cudaMalloc(&jobs.trace, (size_t)grid * sizeof(unsigned long long));
     cudaMemset(jobs.trace, 0, (size_t)grid * sizeof(unsigned long long));
   }
-  launch_k_cluster(tc::k_tc_bwd, grid, tc::kChThreads, tc::kChSmem + 1024, st, 2, jobs);
+  if (chain_sched() == 1) launch_k_cluster(tc::k_tc_bwd<1>, grid, tc::kChThreads, tc::kChSmem + 1024, st, 2, jobs);
+  else launch_k_cluster(tc::k_tc_bwd<0>, grid, tc::kChThreads, tc::kChSmem + 1024, st, 2, jobs);
   BF_LAUNCH(h);
   if (tracing) {
     cudaStreamSynchronize(st);

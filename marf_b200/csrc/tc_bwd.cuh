@@ -229,13 +229,16 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
   }
 }
 
+template <int SCHED>
 __global__ void __launch_bounds__(kChThreads, 1) k_tc_bwd(const __grid_constant__ BwdJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int cluster = (int)blockIdx.x / 2;
   if (jobs.trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) jobs.trace[2 * cluster] = globaltimer_ns();
-  if (cluster < jobs.n_chain_clusters) chain_role<CH_DX, 2>(jobs.chain, smem, cluster, jobs.n_chain_clusters);
-  else dw_pair_role(jobs, smem, cluster - jobs.n_chain_clusters);
+  if (cluster < jobs.n_chain_clusters) {
+    if (SCHED == 1) chain_role_staggered<CH_DX>(jobs.chain, smem, cluster, jobs.n_chain_clusters);
+    else chain_role<CH_DX, 2>(jobs.chain, smem, cluster, jobs.n_chain_clusters);
+  } else dw_pair_role(jobs, smem, cluster - jobs.n_chain_clusters);
   if (jobs.trace && threadIdx.x == 0 && (blockIdx.x & 1) == 0) jobs.trace[2 * cluster + 1] = globaltimer_ns();
 }
 

@@ -480,11 +480,313 @@ __device__ __forceinline__ void chain_role(const ChainJobs& jobs, uint8_t* smem,
   }
 }
 
-template <int MODE, int CL>
+// ================================================================================================================
+// The same chain on CTA pairs with a TILE-STAGGERED, full-width schedule (SCHED = 1):
+//   every layer of a tile is ONE accumulator of 256 columns (acc[tile] = 256 of the CTA's 512 TMEM columns) filled by N = 256 MMAs,
+//   and the two tiles of a CTA alternate: while the epilogue group of tile 0 drains and rewrites tile 0's slabs, the MMAs of tile 1
+//   run, and vice versa.  Against the two-halves schedule above (both tiles in lockstep, N = 128 halves) this
+//     * reads the A operand once per layer instead of once per half (SMEM: 352 -> 320 KB per tile-layer),
+//     * has no layer-boundary bubble (the other tile's MMAs fill it) and needs no slab hand-over barrier (all MMAs that read a
+//       tile's slabs have completed when its accumulator is complete),
+//     * issues a quarter of the MMA instructions (one issuer thread suffices),
+//   and pays with streaming every layer's weights twice per work item (once per tile; L2 -> SMEM 128 KB per layer per CTA).
+// Barriers: w_full/w_empty [3 stages of 16 KB: this CTA's 128 of the 256 weight rows x 64 K], in_full/in_empty, acc_full[tile],
+// epi_done[tile] (the tile's slabs are rewritten and its accumulator is drained: 4 warps of each CTA).
+template <int MODE>
+__device__ __forceinline__ void chain_role_staggered(const ChainJobs& jobs, uint8_t* smem, const int cid, const int ncl) {
+  constexpr bool kOut = MODE == CH_FWD;
+  constexpr int kStages = 3;
+  constexpr uint32_t kStageBytes = 128 * 128;       // [128 weight rows x 64 K] bf16 per CTA
+  const uint32_t s_act = smem_u32(smem + kChActOff);
+  const uint32_t s_w = smem_u32(smem + kChWOff);
+  const uint32_t s_in = smem_u32(smem + kChInOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kChBarOff);
+  uint64_t* w_full = bars;                       // [3]
+  uint64_t* w_empty = bars + 3;                  // [3]
+  uint64_t* in_full = bars + 6;
+  uint64_t* in_empty = bars + 7;
+  uint64_t* acc_full = bars + 8;                 // [2]  (per tile)
+  uint64_t* epi_done = bars + 10;                // [2]  (per tile)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  constexpr int kGroup = 4;                                             // tiles per work item (two per CTA)
+  const int n_pairs = (jobs.n_tiles + kGroup - 1) / kGroup;
+  const int n_items = n_pairs * jobs.n;
+  const bool ilv = jobs.interleave != 0;
+  auto chain_of = [&](int item) -> int { return ilv ? item % jobs.n : item / n_pairs; };
+  auto group_of = [&](int item) -> int { return ilv ? item / jobs.n : item % n_pairs; };
+
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < jobs.n; ++c) {
+      prefetch_tmap(&jobs.c[c].tmIn);
+      for (int u = 0; u < kChUnits; ++u) { prefetch_tmap(&jobs.c[c].u[u].tmW); prefetch_tmap(&jobs.c[c].u[u].tmOut); }
+      if (kOut) prefetch_tmap(&jobs.c[c].tmWout);
+    }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    mbar_init(in_full, 1);
+    mbar_init(in_empty, 1);
+    for (int t = 0; t < 2; ++t) { mbar_init(&acc_full[t], 1); mbar_init(&epi_done[t], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // PDL: everything below consumes the previous kernels' output
+  if (MODE == CH_FWD) {
+    float* sb = reinterpret_cast<float*>(smem + kChBiasOff);
+    for (int i = threadIdx.x; i < jobs.n * kChUnits * 256; i += kChThreads)
+      sb[i] = jobs.c[i >> 10].u[(i >> 8) & 3].bias[i & 255];
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t wit = 0, n_in = 0;
+      auto load_w = [&](const CUtensorMap* tm, int k) {          // this CTA's 128 of the 256 weight rows, K chunk k
+        const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
+        mbar_wait(&w_empty[s], ph ^ 1);
+        if (rank == 0) mbar_expect_tx(&w_full[s], 2 * kStageBytes);
+        tma_load_2d_2sm(smem + kChWOff + s * kStageBytes, tm, k * kChunkK, (int)rank * 128, &w_full[s], kEvictLast);
+        ++wit;
+      };
+      auto load_in = [&](int item) {
+        const ChainJob& J = jobs.c[chain_of(item)];
+        const int g0 = kGroup * group_of(item);
+        const int tile0 = g0 + 2 * (int)rank;
+        const int n_valid = min(kGroup, jobs.n_tiles - g0);
+        mbar_wait(in_empty, (n_in & 1) ^ 1);
+        if (rank == 0) mbar_expect_tx(in_full, (uint32_t)n_valid * kChSlab);
+        for (int t = 0; t < 2; ++t)
+          if (tile0 + t < jobs.n_tiles) tma_load_2d_2sm(smem + kChInOff + t * kChSlab, &J.tmIn, 0, (tile0 + t) * kTileM, in_full, kEvictFirst);
+        ++n_in;
+      };
+      if (cid < n_items) load_in(cid);
+      for (int item = cid; item < n_items; item += ncl) {
+        const ChainJob& J = jobs.c[chain_of(item)];
+        for (int u = 0; u < kChUnits; ++u) {
+          for (int t = 0; t < 2; ++t)
+            for (int k = 0; k < (u == 0 ? 1 : 4); ++k) load_w(&J.u[u].tmW, k);
+          // the next item's input as soon as unit 0 of this item has consumed the buffer (in_empty): long before it is needed
+          if (u == 1 && item + ncl < n_items) load_in(item + ncl);
+        }
+        if (kOut) {                                   // the output layer's hi/lo rows: this CTA's 8 of 16, 1 KB per K chunk
+          const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
+          mbar_wait(&w_empty[s], ph ^ 1);
+          if (rank == 0) mbar_expect_tx(&w_full[s], 4 * 2048);
+          for (int k = 0; k < 4; ++k)
+            tma_load_2d_2sm(smem + kChWOff + s * kStageBytes + k * 1024, &J.tmWout, k * kChunkK, (int)rank * 8, &w_full[s], kEvictLast);
+          ++wit;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA, one thread)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = idesc_bf16(256, 256, 0, 0);
+      constexpr uint32_t idesc_out = idesc_bf16(256, 16, 0, 0);
+      uint32_t wit = 0, n_in = 0, c_epi[2] = {0u, 0u};
+      bool first_item = true;
+      for (int item = cid; item < n_items; item += ncl, first_item = false) {
+        mbar_wait(in_full, n_in & 1);
+        ++n_in;
+        tc_fence_after();
+        for (int u = 0; u < kChUnits; ++u) {
+          for (uint32_t t = 0; t < 2; ++t) {
+            if (!(first_item && u == 0)) {           // tile t's previous epilogue: slabs rewritten, accumulator drained
+              mbar_wait(&epi_done[t], c_epi[t] & 1);
+              ++c_epi[t];
+              tc_fence_after();
+            }
+            const int nk = u == 0 ? 1 : 4;
+            for (int k = 0; k < nk; ++k) {
+              const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
+              mbar_wait(&w_full[s], ph);
+              tc_fence_after();
+              const uint32_t a = u == 0 ? s_in + t * kChSlab : s_act + (t * 4 + (uint32_t)k) * kChSlab;
+              const uint64_t da = smem_desc_sw128(a, 16, 1024);
+              const uint64_t db = smem_desc_sw128(s_w + s * kStageBytes, 16, 1024);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(tmem_base + t * 256, da + 2 * j, db + 2 * j, idesc, (k | j) != 0);
+              umma_commit_2sm(&w_empty[s]);
+              ++wit;
+            }
+            umma_commit_2sm(&acc_full[t]);
+          }
+          if (u == 0) umma_commit_2sm(in_empty);
+        }
+        if (kOut) {
+          // output layer: N = 16 (rows 0..7 hi, 8..15 lo halves of the <= 4 real output rows) into columns 0..15 of acc[tile]
+          const uint32_t s = wit % kStages, ph = (wit / kStages) & 1;
+          mbar_wait(&w_full[s], ph);
+          tc_fence_after();
+          for (uint32_t t = 0; t < 2; ++t) {
+            mbar_wait(&epi_done[t], c_epi[t] & 1);
+            ++c_epi[t];
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = smem_desc_sw128(s_act + (t * 4 + k) * kChSlab, 16, 1024);
+              const uint64_t db = smem_desc_sw128(s_w + s * kStageBytes + k * 1024, 16, 1024);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) umma_bf16_2sm(tmem_base + t * 256, da + 2 * j, db + 2 * j, idesc_out, (k | j) != 0);
+            }
+            umma_commit_2sm(&acc_full[t]);
+          }
+          umma_commit_2sm(&w_empty[s]);
+          ++wit;
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------ epilogue: group = tile of the CTA, thread = row
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const bool gleader = threadIdx.x == 64 + 128 * grp;
+    const uint32_t sw_row = (uint32_t)(r >> 3) * 1024 + (uint32_t)(r & 7) * 128;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256;
+    uint32_t c_acc = 0;
+    uint32_t* pend_flag = nullptr;       // (group leader) flag of the newest stored tile that is not published yet
+    const uint32_t epi_bar = mapa_u32(smem_u32(&epi_done[grp]), 0);       // the leader CTA's epi_done[tile]
+    for (int item = cid; item < n_items; item += ncl) {
+      const int chain = chain_of(item);
+      const ChainJob& J = jobs.c[chain];
+      const int tile = kGroup * group_of(item) + 2 * (int)rank + grp;
+      const bool valid = tile < jobs.n_tiles;
+      const size_t grow = (size_t)tile * kTileM + r;
+      for (int u = 0; u < kChUnits; ++u) {
+        const ChainUnit& U = J.u[u];
+        uint4 mb0 = make_uint4(0u, 0u, 0u, 0u), mb1 = mb0;
+        if (MODE == CH_DX && valid) {
+          mb0 = *reinterpret_cast<const uint4*>(U.bits + grow * J.bits_ld);
+          mb1 = *reinterpret_cast<const uint4*>(U.bits + grow * J.bits_ld + 4);
+        }
+        mbar_wait(&acc_full[grp], c_acc & 1);
+        ++c_acc;
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (valid) {
+            // the TMA stores that read slabs 2h, 2h+1 (this group's second-newest commit group) must have finished reading
+            if (gleader) bulk_wait_read<1>();
+            named_bar_sync(1 + grp, 128);
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+              const int j = 2 * h + jj;
+              uint32_t v[64];
+              {
+                uint32_t (&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+                uint32_t (&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
+                tmem_ld32(t_lane + j * 64, v0);
+                tmem_ld32(t_lane + j * 64 + 32, v1);
+              }
+              const uint32_t ob = s_act + (uint32_t)(grp * 4 + j) * kChSlab + sw_row;
+              uint32_t obits[2] = {0u, 0u};
+              const uint4 mbh = h == 0 ? mb0 : mb1;
+              const uint32_t mw[2] = {jj == 0 ? mbh.x : mbh.z, jj == 0 ? mbh.y : mbh.w};
+              const uint32_t bp = smem_u32(smem + kChBiasOff) + (uint32_t)((chain * kChUnits + u) * 256 + j * 64) * 4;
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint32_t w[4];
+                float bv[8];
+                if (MODE == CH_FWD) {
+                  const float4 b0 = lds128f(bp + i * 32), b1 = lds128f(bp + i * 32 + 16);
+                  bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+                }
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr) {
+                  const int c = i * 8 + pr * 2;             // column inside the slab
+                  const int tt = (c & 31) >> 1;             // pair index inside the 32-column group
+                  float lo = __uint_as_float(v[c]), hi = __uint_as_float(v[c + 1]);
+                  if (MODE == CH_FWD) {
+                    lo += bv[pr * 2];
+                    hi += bv[pr * 2 + 1];
+                    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                    uint32_t gt;
+                    asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(gt) : "r"(w[pr]), "r"(0u));
+                    obits[c >> 5] |= gt & (0x00010001u << tt);
+                  } else {
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[pr]) : "f"(hi), "f"(lo));
+                    const uint32_t sel = (mw[c >> 5] >> tt) & 0x00010001u;
+                    w[pr] &= sel * 0xFFFFu;
+                  }
+                }
+                sts128(ob + (((uint32_t)i ^ (uint32_t)(r & 7)) << 4), w[0], w[1], w[2], w[3]);
+              }
+              if (MODE == CH_FWD)
+                *reinterpret_cast<uint2*>(U.bits + grow * J.bits_ld + j * 2) = make_uint2(obits[0], obits[1]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(3 + grp, 128);                  // all 128 rows of both slabs are in SMEM
+            if (gleader) {
+              const uint64_t pol = MODE == CH_FWD ? kEvictFirst : (jobs.store_last ? kEvictLast : kEvictNormal);
+              tma_store_2d_hint(&U.tmOut, (2 * h) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h) * kChSlab, pol);
+              tma_store_2d_hint(&U.tmOut, (2 * h + 1) * 64, tile * kTileM, smem + kChActOff + (grp * 4 + 2 * h + 1) * kChSlab, pol);
+              bulk_commit();
+              if (MODE == CH_DX && jobs.ready && h == 1) {
+                // lagged hand-over to the dW pairs (see chain_role)
+                if (pend_flag) {
+                  bulk_wait<2>();
+                  fence_proxy_async_all();
+                  st_release_gpu(pend_flag, jobs.epoch);
+                }
+                pend_flag = jobs.ready + ((size_t)(chain * kChUnits + u) * jobs.n_tiles + tile);
+              }
+            }
+          }
+        }
+        // the MMA warp may read the tile's slabs / overwrite its accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(epi_bar);
+      }
+      if (kOut) {
+        mbar_wait(&acc_full[grp], c_acc & 1);
+        ++c_acc;
+        tc_fence_after();
+        if (valid) {
+          uint32_t v[16];
+          tmem_ld16(t_lane, v);
+          tmem_ld_wait();
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[e] = e < J.k_out ? __uint_as_float(v[e]) + __uint_as_float(v[8 + e]) + __ldg(J.bias_out + e) : 0.f;
+          *reinterpret_cast<float4*>(J.logits + grow * 4) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(epi_bar);
+      }
+    }
+    if (gleader) {
+      bulk_wait<0>();
+      if (MODE == CH_DX && pend_flag) {
+        fence_proxy_async_all();
+        st_release_gpu(pend_flag, jobs.epoch);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();        // the peer may still signal this CTA's barriers / read its SMEM until here
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// SCHED 0: two 128-column halves per layer, both tiles in lockstep (chain_role); SCHED 1: tile-staggered N = 256 (CTA pairs only)
+template <int MODE, int CL, int SCHED = 0>
 __global__ void __launch_bounds__(kChThreads, 1) k_tc_chain(const __grid_constant__ ChainJobs jobs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  chain_role<MODE, CL>(jobs, smem, (int)blockIdx.x / CL, (int)gridDim.x / CL);
+  if (SCHED == 1 && CL == 2) chain_role_staggered<MODE>(jobs, smem, (int)blockIdx.x / CL, (int)gridDim.x / CL);
+  else chain_role<MODE, CL>(jobs, smem, (int)blockIdx.x / CL, (int)gridDim.x / CL);
 }
 
 }  // namespace tc
