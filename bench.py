@@ -141,7 +141,7 @@ def kernel_tables(wl):
 
 def load_traffic(workload_key, precision):
     """DRAM bytes per launch per kernel from the committed ncu capture (profiles/r02_kernel_traffic.json), when it holds this workload."""
-    for name in ("r02_kernel_traffic.json", "r01_kernel_traffic.json"):
+    for name in ("r02_kernel_traffic.json", "r02_kernel_traffic_config2.json", "r01_kernel_traffic.json"):
         tp = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tp):
             tj = json.load(open(tp))

@@ -1,51 +1,82 @@
-"""Turn the raw captures of profiles/tools/refresh_gpu.sh (gpurun_out/) into the tracked artifacts under profiles/:
-r01_launches_bf16_config2.csv (raw launch list), r01_step_kernels_bf16_config2.csv (per-kernel summary of one step),
-r01_top_kernels_full.txt (selected metrics of the --set full capture), r01_kernel_traffic.json (DRAM bytes per launch, read by
-bench.py for roofline.traffic), r01_bench_config2.json (the bench line)."""
-import csv, json, os, shutil, subprocess, sys
+"""Turn the raw captures of profiles/tools/refresh_gpu.sh (gpurun_out/) into the tracked round-2 artifacts under profiles/:
+r02_launches_config{2,4}.csv (raw ncu launch lists), r02_step_kernels_config{2,4}.csv (per-kernel summary of one config-2 step /
+one 2^20-pixel chunk of config 4), r02_top_kernels_full.txt (selected metrics of the --set full capture), r02_kernel_traffic.json
+(DRAM bytes per launch, read by bench.py for roofline.traffic), r02_bench.json (the default bench line)."""
+import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
-shutil.copy(os.path.join(G, "launches_final.csv"), os.path.join(P, "r01_launches_bf16_config2.csv"))
-shutil.copy(os.path.join(G, "bench_final.json"), os.path.join(P, "r01_bench_config2.json"))
-summ = subprocess.run([sys.executable, os.path.join(P, "tools", "summarize_launches.py"), os.path.join(G, "launches_final.csv")],
-                      capture_output=True, text=True, check=True).stdout
-open(os.path.join(P, "r01_step_kernels_bf16_config2.csv"), "w").write(summ)
-raw = subprocess.run(["ncu", "-i", os.path.join(G, "top_kernels_final.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr, rows = rows[0], rows[1:]
+    ix = {h: i for i, h in enumerate(hdr)}
+    per = collections.OrderedDict()
+    for r in rows:
+        per.setdefault((r[ix["ID"]], r[ix["Kernel Name"]]), {})[r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", ""))
+    return [(k[1].split("(")[0].replace("void ", "").replace("marf::", "").replace("tc::", ""), v) for k, v in per.items()]
+
+
+def summary(seg, title):
+    out = [title, "kernel,us,share_pct,dram_read_MB,dram_write_MB,dram_GB/s,l2_MB,l2_TB/s,l2_hit_pct,tensor_pipe_pct"]
+    tot = sum(v.get("gpu__time_duration.sum", 0) for _, v in seg) / 1e3
+    for n, v in seg:
+        us = v.get("gpu__time_duration.sum", 0) / 1e3
+        rd, wr, l2 = v.get("dram__bytes_read.sum", 0), v.get("dram__bytes_write.sum", 0), v.get("lts__t_bytes.sum", 0)
+        out.append(f'{n},{us:.1f},{100 * us / tot:.1f},{rd / 1e6:.1f},{wr / 1e6:.1f},{(rd + wr) / us / 1e3:.0f},{l2 / 1e6:.0f},{l2 / us / 1e6:.1f},'
+                   f'{v.get("lts__t_sector_hit_rate.pct", 0):.1f},{v.get("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", 0):.1f}')
+    rd = sum(v.get("dram__bytes_read.sum", 0) for _, v in seg)
+    wr = sum(v.get("dram__bytes_write.sum", 0) for _, v in seg)
+    out.append(f"TOTAL,{tot:.1f},100,{rd / 1e6:.1f},{wr / 1e6:.1f},{(rd + wr) / tot / 1e3:.0f},,,,")
+    return "\n".join(out) + "\n", rd + wr
+
+
+traffic = {}
+for cfg in ("config2", "config4"):
+    src = os.path.join(G, f"launches_r02_{cfg}.csv")
+    shutil.copy(src, os.path.join(P, f"r02_launches_{cfg}.csv"))
+    L = launches(src)
+    if cfg == "config2":
+        st = [i for i, (n, _) in enumerate(L) if "k_pack_table" in n]
+        seg = L[st[-2]:st[-1]]
+        title = "# one training step of config 2 (216,000 px-samples, image MLP + mask head + edge term), bf16; ncu --clock-control none (cold-cache, serialised: compare shares)"
+    else:
+        st = [i for i, (n, _) in enumerate(L) if "k_encode" in n]
+        seg = L[st[2]:st[3]]
+        title = "# one 2^20-pixel chunk of config 4 (64 chunks per step; image MLP, disk masks), bf16; ncu --clock-control none"
+    txt, tot = summary(seg, title)
+    open(os.path.join(P, f"r02_step_kernels_{cfg}.csv"), "w").write(txt)
+    print(txt)
+    names = {"k_tc_chain<0": "k_tc_chain<fwd>", "k_tc_chain<1": "k_tc_chain<dx>", "k_tc_bwd": "k_tc_bwd", "k_tc_dw": "k_tc_dw", "k_tc_gemm<64, 3": "k_tc_gemm<64,warp_grad>"}
+    traffic[cfg] = {}
+    for n, v in seg:
+        for key, nice in names.items():
+            if key in n:
+                traffic[cfg][nice] = int(v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0))
+for cfg, t in traffic.items():
+    json.dump({"workload": cfg, "precision": "bf16",
+               "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch of each kernel inside a training step (profiles/r02_step_kernels_{cfg}.csv)",
+               "dram_bytes_per_launch": t}, open(os.path.join(P, "r02_kernel_traffic.json" if cfg == "config4" else "r02_kernel_traffic_config2.json"), "w"), indent=1)
+shutil.copy(os.path.join(G, "bench_r02_final.json"), os.path.join(P, "r02_bench.json"))
+
+raw = subprocess.run(["ncu", "-i", os.path.join(G, "r02_top_kernels.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
-keep = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum',
+keep = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor_subpipe_hmma.sum',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__cluster_dim_x', 'launch__shared_mem_per_block_dynamic', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__cycles_active.avg', 'sm__cycles_elapsed.max', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed.sum']
-mult = {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1}
-out = ["ncu --set full --import-source on --clock-control none, the three dominant kernels of ONE training step (config2, bf16), B200,",
-       "round-1 final code; report: gpurun_out/top_kernels_final.ncu-rep (not tracked).  Times are cold-cache and serialised",
+out = ["ncu --set full --import-source on --clock-control none: the two dominant kernels of ONE training step (config 2, bf16), B200,",
+       "round-2 final code; report: gpurun_out/r02_top_kernels.ncu-rep (not tracked).  Times are cold-cache and serialised",
        "(bench.py kernels[] has the in-step CUDA-event times)."]
-traffic = {}
-names = {"k_tc_chain<0": "k_tc_chain<fwd>", "k_tc_chain<1": "k_tc_chain<dx>", "k_tc_dw": "k_tc_dw"}
 for r in rows[2:]:
-    name = r[hdr.index('Kernel Name')]
-    out += ["", "==  " + name]
-    d = {}
+    out += ["", "==  " + r[hdr.index('Kernel Name')]]
     for i, h in enumerate(hdr):
         if h in keep:
             out.append('   %-80s %s %s' % (h, r[i], units[i]))
-            d[h] = (float(r[i].replace(",", "")), units[i])
-    b = lambda k: d[k][0] * mult[d[k][1]]
-    for key, nice in names.items():
-        if key in name:
-            traffic[nice] = int(b('dram__bytes_read.sum') + b('dram__bytes_write.sum'))
-for line in summ.splitlines():
-    if "k_tc_gemm<64, 3" in line:
-        f = line.split(",")
-        traffic["k_tc_gemm<64,warp_grad>"] = int((float(f[-5]) + float(f[-4])) * 1e6)
-open(os.path.join(P, "r01_top_kernels_full.txt"), "w").write("\n".join(out) + "\n")
-json.dump({"workload": "config2", "precision": "bf16",
-           "source": "ncu --set full --clock-control none, one capture of one training step (profiles/r01_top_kernels_full.txt; the "
-                     "warp-grad GEMM from the --metrics launch list); dram__bytes_read.sum + dram__bytes_write.sum per launch",
-           "dram_bytes_per_launch": traffic}, open(os.path.join(P, "r01_kernel_traffic.json"), "w"), indent=1)
-print(summ)
-print(json.dumps(traffic))
+open(os.path.join(P, "r02_top_kernels_full.txt"), "w").write("\n".join(out) + "\n")
+print("\n".join(out[-30:]))
