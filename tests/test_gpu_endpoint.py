@@ -1,11 +1,12 @@
-"""End-point parity, short version (SURVEY §8 row g): 300 iterations of the training loop (model/planar.py:136-209) at the MID
-size, this library in both precisions against the oracle port on the same GPU, same scene, same init.
+"""End-point parity, short version (SURVEY §8 row g): 400 iterations of the training loop (model/planar.py:136-209) at the MID
+size from a small misalignment (noise_h 0.03, noise_t 0.05: the run registers to ~0.2 px within the 400 iterations), this library
+in both precisions against the oracle port on the same GPU, same scene, same init.
 The full 3000-iteration run is profiles/r02_endpoint_parity.{json,txt} (tests/endpoint_parity.py).
 
-Tolerances: the run is still early (5.5 px) after 300 iterations and Adam amplifies last-bit differences — the oracle's own
-fp32 and fp64 runs end 0.06 px / 0.02 dB apart here (0.6 dB apart after 3000 iterations at full size) — so the bound is
-0.25 px / 0.5 dB in fp32 (observed over three runs: 0.05-0.09 px, 0.12-0.13 dB) and 0.25 px / 1.0 dB in bf16 (0.04-0.07 px,
-0.24-0.57 dB: the weight gradients are summed with fp32 reductions whose order changes from run to run)."""
+Tolerances: Adam amplifies last-bit differences, and the weight gradients are summed with reductions whose order changes from run
+to run.  Observed over three runs: oracle fp32 0.177 px / 34.54 dB, oracle fp64 0.210 / 34.12, this library fp32 0.226-0.236 px /
+34.23-34.26 dB, bf16 0.158-0.207 px / 33.96-34.41 dB — i.e. deviations from the oracle of <= 0.06 px and <= 0.6 dB, the size of the
+oracle's own fp32-vs-fp64 difference (0.03 px / 0.4 dB).  Bounds: 0.12 px (BASELINE's criterion is 0.1 px at max_iter) and 1.0 dB."""
 import argparse
 
 import pytest
@@ -15,15 +16,16 @@ pytestmark = pytest.mark.gpu
 
 def test_endpoint_short_run_matches_oracle():
     import endpoint_parity as ep
-    args = argparse.Namespace(batch=3, noise_h=0.1, noise_t=0.2, scene_seed=0, torch_adam=False)
-    res = ep.run_scene("c1", 300, 72, 96, ["repo_fp32", "repo_bf16", "oracle_fp32", "oracle_fp64"], args, every=100)
+    args = argparse.Namespace(batch=3, noise_h=0.03, noise_t=0.05, scene_seed=0, torch_adam=False)
+    res = ep.run_scene("c1", 400, 72, 96, ["repo_fp32", "repo_bf16", "oracle_fp32", "oracle_fp64"], args, every=100)
     ref = res["oracle_fp32"]
-    assert ref["hist"][0]["corner_px"] > 5.0 and ref["corner_px"] < ref["hist"][0]["corner_px"]     # the run registers
+    assert ref["hist"][0]["corner_px"] > 1.0 and ref["corner_px"] < 0.4          # the run registers
     for arm in ("repo_fp32", "repo_bf16", "oracle_fp64"):
         d = res[arm]["delta_vs_oracle_fp32"]
-        print(arm, d)
-        assert d["corner_px"] <= 0.25, (arm, d)
-        assert d["psnr_last200"] <= (1.0 if arm == "repo_bf16" else 0.5), (arm, d)
+        print(arm, res[arm]["corner_px"], res[arm]["psnr_last200"], d)
+        assert res[arm]["corner_px"] < 0.4, (arm, res[arm]["corner_px"])
+        assert d["corner_px"] <= 0.12, (arm, d)
+        assert d["psnr_last200"] <= 1.0, (arm, d)
     # the first iteration is a single step from identical parameters: losses agree to fp32 / bf16 step precision
     assert abs(res["repo_fp32"]["hist"][0]["loss"] - ref["hist"][0]["loss"]) <= 2e-5 * abs(ref["hist"][0]["loss"])
     assert abs(res["repo_bf16"]["hist"][0]["loss"] - ref["hist"][0]["loss"]) <= 2e-2 * abs(ref["hist"][0]["loss"])
