@@ -11,14 +11,19 @@ import torch
 from . import _lib as L
 
 
-def shard_plan(batch_global: int, h: int, rank: int, world: int):
+def shard_plan(batch_global: int, h: int, rank: int, world: int, whole_patches: bool = False):
     """whole patches per rank when they divide evenly, else an equal row range of every patch.
+    `whole_patches` (the edge term needs whole patches: its Sobel/Gauss stencils read 3 rows of halo): patches are dealt out as
+    evenly as they go instead, the first `batch_global % world` ranks take one more, and a rank may end up with none (batch 0).
     Returns (batch, patch_offset, rows, row_offset)."""
     if world <= 1:
         return batch_global, 0, h, 0
     if batch_global % world == 0:
         per = batch_global // world
         return per, rank * per, h, 0
+    if whole_patches:
+        base, extra = divmod(batch_global, world)
+        return base + (1 if rank < extra else 0), rank * base + min(rank, extra), h, 0
     base, extra = divmod(h, world)
     rows = base + (1 if rank < extra else 0)
     row_offset = rank * base + min(rank, extra)
@@ -42,7 +47,12 @@ class PlanarEngine:
         w = patch_W if use_cropped else W
         self.h, self.w = h, w
         self.batch_global = batch_size
-        self.batch, self.patch_offset, self.rows, self.row_offset = shard_plan(batch_size, h, rank, world)
+        self.batch, self.patch_offset, self.rows, self.row_offset = shard_plan(batch_size, h, rank, world, whole_patches=bool(use_edges))
+        # a rank that was dealt no patch (more ranks than patches, whole-patch sharding) still needs a handle for the replicated
+        # optimizer step and the renders: it evaluates patch 0 and its contributions are zeroed before the exchange (Graph.forward)
+        self.idle = self.batch == 0
+        if self.idle:
+            self.batch, self.patch_offset = 1, 0
         self.rank, self.world = rank, world
         self.mask_mode = mask_mode
         self.use_edges = bool(use_edges)

@@ -258,6 +258,8 @@ class Graph(torch.nn.Module):
             if self.opt.use_masks:
                 s = torch.stack([loc.masks.double().sum(),
                                  loc.masks_eroded.double().sum() if loc.masks_eroded is not None else torch.zeros((), dtype=torch.float64, device=e.device)])
+                if e.idle:                     # (a rank without a patch of its own contributes nothing)
+                    s.zero_()
                 dist.all_reduce(s)
                 n_rgb, n_edge = 3.0 * float(s[0]), 3.0 * float(s[1])
             else:
@@ -266,6 +268,13 @@ class Graph(torch.nn.Module):
         self._local = (key, loc)
         e.bump_data_version()
         return loc
+
+    def _zero_contribution(self, sums, grads):
+        """A rank that holds no patch of its own (engine.idle) evaluated patch 0 as a stand-in: drop what it computed."""
+        if sums is not None:
+            sums.zero_()
+        if grads:
+            (self._peer.grad_local if self._peer_grads else self._grad_flat).zero_()
 
     def _allreduce(self, sums, grads):
         """The exchange step of data parallelism: loss sums (in place) and / or the flat gradient buffer."""
@@ -324,11 +333,17 @@ class Graph(torch.nn.Module):
         elif not implicit:
             kw["norm_rgb"], kw["norm_edge"] = self._norms
             sums = e.step(**kw)
+            if e.idle:
+                self._zero_contribution(sums, grads=True)
             self._allreduce(sums, grads=True)
         else:
             sums = e.step_forward(**kw)
+            if e.idle:
+                self._zero_contribution(sums, grads=False)
             self._allreduce(sums, grads=False)
             e.step_backward()
+            if e.idle:
+                self._zero_contribution(None, grads=True)
             self._allreduce(None, grads=True)
         self._sums = sums
         B = e.batch

@@ -31,6 +31,10 @@ def main():
         "nomask_rows": dict(batch_size=3, use_masks=False, use_implicit_mask=False, use_edges=False),
         "implicit_patches_edges": dict(batch_size=world, use_masks=True, use_implicit_mask=True, use_edges=True,
                                        H=360, W=480, patch_H=180, patch_W=240),
+        # the edge term needs whole patches: uneven deal (one rank takes two), and more ranks than patches (the last rank idles)
+        "disk_edges_uneven": dict(batch_size=world + 1, use_masks=True, use_implicit_mask=False, use_edges=True),
+        "implicit_edges_idle_rank": dict(batch_size=world - 1, use_masks=True, use_implicit_mask=True, use_edges=True,
+                                         H=360, W=480, patch_H=180, patch_W=240),
     }.items():
         if case.endswith("rows") and 3 % world == 0:
             over["batch_size"] = world + 1
@@ -68,7 +72,7 @@ def main():
         tol_g, tol_l = (2e-3, 1e-5) if args.precision == "fp32" else (2e-2, 1e-4)
         ok = gerr <= tol_g and lerr <= tol_l
         e = g.engine
-        print(f"[rank {rank}/{world}] {case}: shard(batch={e.batch}, patch_offset={e.patch_offset}, rows={e.rows}, "
+        print(f"[rank {rank}/{world}] {case}: shard(batch={0 if e.idle else e.batch}, patch_offset={e.patch_offset}, rows={e.rows}, "
               f"row_offset={e.row_offset}) exchange={'peer' if g._peer_grads else ('peer-sums+nccl' if g._peer is not None else 'nccl')} grad rel-L2 err {gerr:.2e}, "
               f"loss rel err {lerr:.2e} {'OK' if ok else 'FAIL'}", flush=True)
         if not ok:

@@ -126,6 +126,11 @@ def test_shard_plan():
     assert sum(p[2] for p in parts) == 180 and parts[0][3] == 0
     for a, b in zip(parts[:-1], parts[1:]):
         assert a[3] + a[2] == b[3]
+    # the edge term needs whole patches: dealt out unevenly, possibly none for the last ranks
+    assert [shard_plan(5, 180, r, 2, whole_patches=True) for r in range(2)] == [(3, 0, 180, 0), (2, 3, 180, 0)]
+    parts = [shard_plan(5, 180, r, 8, whole_patches=True) for r in range(8)]
+    assert [p[0] for p in parts] == [1, 1, 1, 1, 1, 0, 0, 0] and [p[1] for p in parts[:5]] == [0, 1, 2, 3, 4]
+    assert shard_plan(64, 1024, 3, 8, whole_patches=True) == (8, 24, 1024, 0)
 
 
 def test_loss_coefficients_match_oracle():

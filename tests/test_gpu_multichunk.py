@@ -56,3 +56,42 @@ def test_step_four_chunks_of_2p20_matches_oracle(precision):
         assert v <= bound, (k, report)
     assert res["nonfinite"] == 0.0
     eng.close()
+
+
+def test_patch_shards_add_up_at_config4_patch_size():
+    """Data-parallel arithmetic at BASELINE config 4's patch size on ONE GPU: 4 patches of 1024x1024 as one 4-chunk step ==
+    the sum of two 2-patch shards (the rank-0 and rank-1 engines of a 2-rank job run one after the other) when both shards use
+    the global loss normaliser — gradients are sums over pixel-samples.  bf16 tensor-core mode; what remains
+    is the order of the fp32 reductions."""
+    import gpu_util
+    from marf_b200 import _lib as L
+    cfg = po.PlanarConfig(H=2048, W=2048, patch_H=1024, patch_W=1024, batch_size=4, use_masks=True, max_iter=3000)
+    params = po.init_params(cfg, seed=3)
+    params.warp = fx.synth_warp(31, 4, scale=0.05)
+    images = cases.make_images(cfg, 41)
+    it, progress = 450, 450 / 3000
+    norm = 3.0 * float(images["masks"].double().sum())
+
+    def run(rank, world):
+        eng = gpu_util.make_engine(cfg, "bf16", rank=rank, world=world)
+        kw = gpu_util.step_kwargs(eng, cfg, params, images, it, progress)
+        lo, n = eng.patch_offset, eng.batch
+        for k in ("rgb", "masks"):
+            kw[k] = kw[k][lo:lo + n].contiguous()
+        kw["rgb_pred"] = torch.zeros(n, cfg.h * cfg.w, 3, device=eng.device)
+        kw["norm_rgb"] = norm
+        eng.step(**kw)
+        torch.cuda.synchronize()
+        flat = torch.cat([t.flatten() for t in kw["g_mlp_w"] + kw["g_mlp_b"] + [kw["g_warp"]]]).double().cpu()
+        sums = eng.sums.clone().cpu()
+        eng.close()
+        return flat, sums
+
+    whole, s_whole = run(0, 1)
+    a, s_a = run(0, 2)
+    b, s_b = run(1, 2)
+    rel = ((a + b - whole).norm() / whole.norm()).item()
+    print("shards vs whole: gradient rel-L2", rel)
+    assert rel <= 2e-5, rel
+    assert abs(float(s_a[L.S_RGB] + s_b[L.S_RGB]) - float(s_whole[L.S_RGB])) <= 1e-9 * float(s_whole[L.S_RGB])
+    assert float(s_a[L.N_RGB] + s_b[L.N_RGB]) == float(s_whole[L.N_RGB])
