@@ -66,6 +66,8 @@ def make_opt(wl, device, precision, out_dir):
     opt.arch.posenc.L_2D = wl["L"]
     opt.synthetic = dict(enabled=True, seed=0, occluders=True)
     opt.fused_optimizer = True
+    if os.environ.get("MARF_BENCH_CHUNK"):              # (experiments: pixel-samples per pass, library default 2^20 in bf16 mode)
+        opt.max_chunk_pixels = int(os.environ["MARF_BENCH_CHUNK"])
     opt.freq.scalar = 10 ** 9
     opt.freq.vis = 10 ** 9
     return opt
