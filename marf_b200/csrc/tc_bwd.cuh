@@ -83,6 +83,7 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
   uint64_t* empty = bars + kBwStages;       // [kBwStages]  (multicast commit: the MMAs that read the stage have completed)
   uint64_t* done = bars + 2 * kBwStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  volatile int* progress = reinterpret_cast<volatile int*>(done + 2);       // the producer's current stage (this CTA)
   const int b_slabs = J.n_cols / 128;       // X slabs this CTA holds (2, or 1 for the 64-wide inputs)
   const uint32_t stage_bytes = (uint32_t)(2 + b_slabs) * kBwSlab;
 
@@ -91,6 +92,7 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
     prefetch_tmap(&J.tmX);
     for (int s = 0; s < kBwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }    // (one commit per issuer)
     mbar_init(done, 2);
+    *progress = 0;
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -110,15 +112,6 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
       // Hand-over flags are read by the WHOLE warp, 32 upcoming stages at a time: one L2 round trip per batch.  (One acquire
       // load per stage in the issuing thread serialises a ~0.7 us round trip into every stage: measured 1.0 us per stage.)
       int n_ok = J.ready ? 0 : n_my;                  // stages [0, n_ok) of this pair are known to be published (warp-uniform)
-      // X_l has been in HBM since the forward pass: pull this pair's tiles into L2 `pf` stages ahead of the SMEM ring, so that
-      // the ring's loads see L2 latency (the ring holds 192 KB per CTA: at ~2.5 us of loaded HBM latency it was latency-bound)
-      const int pf = jobs.prefetch_ahead;
-      auto prefetch_x = [&](int i) {
-        const int row = (k + i * J.pair_count) * kBwRows;
-        for (int b = 0; b < b_slabs; ++b) tma_prefetch_2d(&J.tmX, ((int)rank * b_slabs + b) * 64, row);
-      };
-      if (lane == 0)
-        for (int i = 0; i < pf && i < n_my; ++i) prefetch_x(i);
       for (int i = 0; i < n_my; ++i) {
         if (i >= n_ok) {
           uint32_t spins = 0;
@@ -138,7 +131,7 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
         if (lane == 0) {
           const uint32_t s = i % kBwStages, ph = (i / kBwStages) & 1;
           const int row = (k + i * J.pair_count) * kBwRows;
-          if (i + pf < n_my && pf > 0) prefetch_x(i + pf);
+          *progress = i;                               // (paces the L2 prefetcher, warp 7)
           mbar_wait(&empty[s], ph ^ 1);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
           uint8_t* st = smem + s * kBwStage;
@@ -176,6 +169,23 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
           umma_commit_2sm(&empty[s]);
         }
         umma_commit_2sm(done);
+      }
+    } else if (warp == 7) {
+      // ---------------------------------------------------------------- L2 prefetcher (both CTAs): X_l has been in HBM since the
+      // forward pass; this thread pulls the pair's X tiles into L2 `prefetch_ahead` stages ahead of the producer, so that the SMEM
+      // ring (192 KB per CTA, all there is) sees L2 latency instead of loaded HBM latency.  Its own thread: a prefetch issued by
+      // the producer thread delays that thread's loads (measured).
+      const int pf = jobs.prefetch_ahead;
+      if (lane == 0 && pf > 0) {
+        int j = 0;
+        while (j < n_my) {
+          const int lim = min(n_my, *progress + pf);
+          for (; j < lim; ++j) {
+            const int row = (k + j * J.pair_count) * kBwRows;
+            for (int b = 0; b < b_slabs; ++b) tma_prefetch_2d(&J.tmX, ((int)rank * b_slabs + b) * 64, row);
+          }
+          if (j < n_my) __nanosleep(500);
+        }
       }
     } else if (warp < 6) {
       // ---------------------------------------------------------------- accumulators -> global (both CTAs)
