@@ -1136,27 +1136,36 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
   // each against 128 / 64 cycles of tensor work for N = 256 / 128): equal weights, slightly less for the 64-wide layer-0 inputs
   double weight[tc::kBwdMaxJobs];
   auto add = [&](const CUtensorMap& tmDY, const CUtensorMap& tmX, const uint32_t* ready, int n_cols, int m_valid, int n_valid,
-                 int ld_w, int do_bias, float* dW, float* db) {
+                 int ld_w, int do_bias, float* dW, float* db, int dy_cols, int x_cols) {
     tc::BwdDwJob& D = jobs.dw[jobs.n_dw];
     D.tmDY = tmDY; D.tmX = tmX; D.ready = ready; D.n_cols = n_cols; D.m_valid = m_valid; D.n_valid = n_valid;
-    D.ld_w = ld_w; D.do_bias = do_bias; D.dW = dW; D.db = db;
-    weight[jobs.n_dw++] = n_cols == 256 ? 1.0 : 0.8;
+    D.ld_w = ld_w; D.do_bias = do_bias; D.dW = dW; D.db = db; D.dy_cols = dy_cols; D.x_cols = x_cols;
+    // a stage costs a pair the TMA boxes of its busier CTA (4 for the 256 x 256 jobs, 3 for the output layers and layer 0)
+    int worst = 0;
+    for (int r = 0; r < 2; ++r) {
+      int nb = 0;
+      for (int sl = 0; sl < 2; ++sl) nb += (r * 128 + sl * 64 < dy_cols) ? 1 : 0;
+      for (int b = 0; b < n_cols / 128; ++b) nb += ((r * (n_cols / 128) + b) * 64 < x_cols) ? 1 : 0;
+      worst = std::max(worst, nb);
+    }
+    weight[jobs.n_dw++] = worst / 4.0;
   };
   for (int ci = 0; ci < n_chains; ++ci) {
     BfChain& B = *chains[ci];
     Chain& F = *B.f32;
     const int n = B.n;
     if (jobs.n_dw + n > tc::kBwdMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 backward: too many layers");
-    add(B.tmDL128, B.tmAct128[n - 1], nullptr, 256, B.L[n - 1].k_out, B.L[n - 1].k_in, F.ld_in[n - 1], 1, F.gWp[n - 1], F.gbp[n - 1]);
+    add(B.tmDL128, B.tmAct128[n - 1], nullptr, 256, B.L[n - 1].k_out, B.L[n - 1].k_in, F.ld_in[n - 1], 1, F.gWp[n - 1], F.gbp[n - 1], 8, 256);
     for (int l = n - 2; l >= 0; --l) {
       // dY[l] is the output of chain unit n-2-l
       const uint32_t* ready = S->ready + (size_t)(ci * tc::kChUnits + (n - 2 - l)) * n_tiles;
       if (l == 0 && B.col_off0 > 0)
         // class-table mode: the whole [256, 64] tile (uv columns and per-class sums) goes to the scratch that the tail launch
         // (k_unpack_table modes 1 / 2) turns into dW0 / db0
-        add(B.tmDY128[0], B.tmAct128[0], ready, 128, B.L[0].k_out, 64, 64, 0, B.dW0x, F.gbp[0]);
+        add(B.tmDY128[0], B.tmAct128[0], ready, 128, B.L[0].k_out, 64, 64, 0, B.dW0x, F.gbp[0], 256, 64);
       else
-        add(B.tmDY128[l], B.tmAct128[l], ready, l == 0 ? 128 : 256, B.L[l].k_out, B.L[l].k_in, F.ld_in[l], 1, F.gWp[l], F.gbp[l]);
+        add(B.tmDY128[l], B.tmAct128[l], ready, l == 0 ? 128 : 256, B.L[l].k_out, B.L[l].k_in, F.ld_in[l], 1, F.gWp[l], F.gbp[l], 256,
+            l == 0 ? 64 : 256);
       // (dY[0] of a chain whose input gradient is needed is read again by the warp-gradient GEMM: kept)
       if (discard && !(l == 0 && B.need_dx0)) {
         jobs.dw[jobs.n_dw - 1].dy_base = reinterpret_cast<unsigned char*>(B.dY[l]);
@@ -1166,11 +1175,11 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
   }
   // chain pairs : dW pairs.  Measured on the B200 (profiles/r02_bwd_experiments.md): both roles run ~25 % slower side by side than
   // alone (they share L2 / HBM), a dW pair is bound by its operand loads (~0.85 us per 128-row stage whatever the job), and the
-  // launch is fastest when the two roles finish together: 36 : 38 with two networks (10 jobs), 39 : 35 with one (5 jobs).
+  // launch is fastest when the two roles finish together: 38 : 36 with two networks (10 jobs), 39 : 35 with one (5 jobs).
   // MARF_BWD_CHAIN_CLUSTERS overrides.
   double wsum = 0;
   for (int i = 0; i < jobs.n_dw; ++i) wsum += weight[i];
-  int n_chain = (int)(total_pairs * (n_chains == 2 ? 0.49 : 0.53) + 0.5);
+  int n_chain = (int)(total_pairs * (n_chains == 2 ? 0.515 : 0.53) + 0.5);
   if (const char* e = getenv("MARF_BWD_CHAIN_CLUSTERS")) n_chain = atoi(e);
   const int n_items = (n_tiles + 3) / 4 * n_chains;
   n_chain = std::max(1, std::min(n_chain, std::min(n_items, total_pairs - jobs.n_dw)));

@@ -37,6 +37,8 @@ struct alignas(64) BwdDwJob {
   const uint32_t* ready;  // per-tile flags of the chain unit that produces dY_l (nullptr: complete before the launch)
   int n_cols;             // MMA N: 256, or 128 for the 64-wide inputs (the second CTA's half is TMA out-of-bounds zero fill)
   int m_valid, n_valid;   // real out / in features
+  int dy_cols, x_cols;    // columns the dY / X tensors really have (256, 8 for the dlogits tile, 64 for the encoded inputs): boxes
+                          // that lie wholly beyond them are not loaded (their SMEM slabs stay zero)
   int ld_w;
   int do_bias;
   float* dW;              // [out, ld_w] fp32, accumulated with red.add
@@ -85,7 +87,17 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   volatile int* progress = reinterpret_cast<volatile int*>(done + 2);       // the producer's current stage (this CTA)
   const int b_slabs = J.n_cols / 128;       // X slabs this CTA holds (2, or 1 for the 64-wide inputs)
-  const uint32_t stage_bytes = (uint32_t)(2 + b_slabs) * kBwSlab;
+  // A TMA box costs its 128 rows of TMA-engine time whether it fetches anything or not (measured: the operand loads bound a dW
+  // pair at ~3.3 cycles per 128-byte box row), so boxes that lie wholly outside their tensor are skipped: the slabs are zeroed
+  // once and never written.  real_boxes(r): how many boxes CTA r of the pair loads per stage.
+  auto dy_real = [&](uint32_t r, int sl) { return (int)r * 128 + sl * 64 < J.dy_cols; };
+  auto x_real = [&](uint32_t r, int b) { return ((int)r * b_slabs + b) * 64 < J.x_cols; };
+  int boxes_pair = 0;
+  for (uint32_t r = 0; r < 2; ++r) {
+    for (int sl = 0; sl < 2; ++sl) boxes_pair += dy_real(r, sl) ? 1 : 0;
+    for (int b = 0; b < b_slabs; ++b) boxes_pair += x_real(r, b) ? 1 : 0;
+  }
+  const uint32_t stage_bytes_pair = (uint32_t)boxes_pair * kBwSlab;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&J.tmDY);
@@ -96,6 +108,8 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  for (int i = threadIdx.x; i < kBwStages * kBwStage / 16; i += kChThreads)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   // the constant ones tile (any layout of an all-ones slab is an all-ones operand)
   for (int i = threadIdx.x; i < 8192 / 16; i += kChThreads)
     reinterpret_cast<uint4*>(smem + kBwOnesOff)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -133,13 +147,13 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
           const int row = (k + i * J.pair_count) * kBwRows;
           *progress = i;                               // (paces the L2 prefetcher, warp 7)
           mbar_wait(&empty[s], ph ^ 1);
-          if (rank == 0) mbar_expect_tx(&full[s], 2 * stage_bytes);
+          if (rank == 0) mbar_expect_tx(&full[s], stage_bytes_pair);
           uint8_t* st = smem + s * kBwStage;
-          // dY: this CTA's 128 output features; X: its half of the N columns.  Boxes beyond the tensor's width are zero fill.
-          tma_load_2d_2sm(st, &J.tmDY, (int)rank * 128, row, &full[s], kEvictFirst);
-          tma_load_2d_2sm(st + kBwSlab, &J.tmDY, (int)rank * 128 + 64, row, &full[s], kEvictFirst);
+          // dY: this CTA's 128 output features; X: its half of the N columns (boxes partly beyond the tensor's width: zero fill)
+          for (int sl = 0; sl < 2; ++sl)
+            if (dy_real(rank, sl)) tma_load_2d_2sm(st + sl * kBwSlab, &J.tmDY, (int)rank * 128 + sl * 64, row, &full[s], kEvictFirst);
           for (int b = 0; b < b_slabs; ++b)
-            tma_load_2d_2sm(st + (2 + b) * kBwSlab, &J.tmX, ((int)rank * b_slabs + b) * 64, row, &full[s], kEvictFirst);
+            if (x_real(rank, b)) tma_load_2d_2sm(st + (2 + b) * kBwSlab, &J.tmX, ((int)rank * b_slabs + b) * 64, row, &full[s], kEvictFirst);
         }
         __syncwarp();
       }
