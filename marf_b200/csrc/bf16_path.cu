@@ -1116,6 +1116,8 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
   // write-back once consumed (discard.global.L2): -2.5 % launch time; MARF_BWD_STORE_LAST=0 / MARF_BWD_DISCARD=0 switch them off
   jobs.chain.store_last = getenv("MARF_BWD_STORE_LAST") ? atoi(getenv("MARF_BWD_STORE_LAST")) : 1;
   const bool discard = getenv("MARF_BWD_DISCARD") ? atoi(getenv("MARF_BWD_DISCARD")) != 0 : true;
+  // (measured: no gain — 471 vs 463 us on config 2, 1325 vs 1259 us on config 4; the stage time does not follow the TMA bytes)
+  const bool ldgsts = getenv("MARF_BWD_LDGSTS") ? atoi(getenv("MARF_BWD_LDGSTS")) != 0 : false;
   for (int ci = 0; ci < n_chains; ++ci) {
     BfChain& B = *chains[ci];
     tc::ChainJob& J = jobs.chain.c[ci];
@@ -1156,6 +1158,10 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
     const int n = B.n;
     if (jobs.n_dw + n > tc::kBwdMaxJobs) return fail(h, MARF_ERR_UNSUPPORTED, "bf16 backward: too many layers");
     add(B.tmDL128, B.tmAct128[n - 1], nullptr, 256, B.L[n - 1].k_out, B.L[n - 1].k_in, F.ld_in[n - 1], 1, F.gWp[n - 1], F.gbp[n - 1], 8, 256);
+    if (ldgsts) {
+      jobs.dw[jobs.n_dw - 1].x_base = reinterpret_cast<const unsigned char*>(B.act[n - 1]);
+      jobs.dw[jobs.n_dw - 1].x_pitch = B.ld[n - 1] * 2;
+    }
     for (int l = n - 2; l >= 0; --l) {
       // dY[l] is the output of chain unit n-2-l
       const uint32_t* ready = S->ready + (size_t)(ci * tc::kChUnits + (n - 2 - l)) * n_tiles;
@@ -1166,6 +1172,11 @@ static int launch_bwd(marf_handle* h, cudaStream_t st, BfChain** chains, int n_c
       else
         add(B.tmDY128[l], B.tmAct128[l], ready, l == 0 ? 128 : 256, B.L[l].k_out, B.L[l].k_in, F.ld_in[l], 1, F.gWp[l], F.gbp[l], 256,
             l == 0 ? 64 : 256);
+      // MARF_BWD_LDGSTS=1 (experiment): 256-column X loaded by cp.async beside the TMA loads of dY
+      if (ldgsts && l >= 1) {
+        jobs.dw[jobs.n_dw - 1].x_base = reinterpret_cast<const unsigned char*>(B.act[l]);
+        jobs.dw[jobs.n_dw - 1].x_pitch = B.ld[l] * 2;
+      }
       // (dY[0] of a chain whose input gradient is needed is read again by the warp-gradient GEMM: kept)
       if (discard && !(l == 0 && B.need_dx0)) {
         jobs.dw[jobs.n_dw - 1].dy_base = reinterpret_cast<unsigned char*>(B.dY[l]);

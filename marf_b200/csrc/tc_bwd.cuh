@@ -43,6 +43,8 @@ struct alignas(64) BwdDwJob {
   int do_bias;
   float* dW;              // [out, ld_w] fp32, accumulated with red.add
   float* db;              // [out] fp32
+  const unsigned char* x_base;   // X_l as raw bytes [rows, x_pitch] when this job's X tiles are loaded with cp.async by warps 2..5
+  int x_pitch;                   // (256-column X only) instead of TMA: a second, independent path into SMEM (nullptr: TMA)
   unsigned char* dy_base; // dY_l as raw bytes [rows, dy_pitch] when the tiles may be DISCARDED from L2 once consumed (nullptr: keep)
   int dy_pitch;
   int pair_begin, pair_count;   // dW pairs [pair_begin, pair_begin + pair_count) take this job's 128-row stages round-robin
@@ -95,14 +97,15 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
   int boxes_pair = 0;
   for (uint32_t r = 0; r < 2; ++r) {
     for (int sl = 0; sl < 2; ++sl) boxes_pair += dy_real(r, sl) ? 1 : 0;
-    for (int b = 0; b < b_slabs; ++b) boxes_pair += x_real(r, b) ? 1 : 0;
+    for (int b = 0; b < b_slabs; ++b) boxes_pair += (!J.x_base && x_real(r, b)) ? 1 : 0;
   }
   const uint32_t stage_bytes_pair = (uint32_t)boxes_pair * kBwSlab;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&J.tmDY);
     prefetch_tmap(&J.tmX);
-    for (int s = 0; s < kBwStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); }    // (one commit per issuer)
+    // full: the producer's arrive (+ TMA bytes) and, with the cp.async path for X, one arrive per loader warp of both CTAs
+    for (int s = 0; s < kBwStages; ++s) { mbar_init(&full[s], J.x_base ? 9 : 1); mbar_init(&empty[s], 2); }    // (empty: one commit per issuer)
     mbar_init(done, 2);
     *progress = 0;
     fence_barrier_init();
@@ -152,8 +155,9 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
           // dY: this CTA's 128 output features; X: its half of the N columns (boxes partly beyond the tensor's width: zero fill)
           for (int sl = 0; sl < 2; ++sl)
             if (dy_real(rank, sl)) tma_load_2d_2sm(st + sl * kBwSlab, &J.tmDY, (int)rank * 128 + sl * 64, row, &full[s], kEvictFirst);
-          for (int b = 0; b < b_slabs; ++b)
-            if (x_real(rank, b)) tma_load_2d_2sm(st + (2 + b) * kBwSlab, &J.tmX, ((int)rank * b_slabs + b) * 64, row, &full[s], kEvictFirst);
+          if (!J.x_base)
+            for (int b = 0; b < b_slabs; ++b)
+              if (x_real(rank, b)) tma_load_2d_2sm(st + (2 + b) * kBwSlab, &J.tmX, ((int)rank * b_slabs + b) * 64, row, &full[s], kEvictFirst);
         }
         __syncwarp();
       }
@@ -202,21 +206,58 @@ __device__ __forceinline__ void dw_pair_role(const BwdJobs& jobs, uint8_t* smem,
         }
       }
     } else if (warp < 6) {
-      // ---------------------------------------------------------------- accumulators -> global (both CTAs)
+      // ---------------------------------------------------------------- warps 2..5 (both CTAs): X loader, L2 discard, read-out
       const int q = warp & 3;
       const int r = q * 32 + lane;
       const int m = (int)rank * 128 + r;
-      if (J.dy_base) {
-        // Nobody reads a dY tile again once its MMAs have completed: drop this CTA's half of it (128 rows x 256 B) from L2
-        // without a write-back (discard.global.L2), so that the hand-over costs no DRAM write either.
-        for (int i = 0; i < n_my; ++i) {
-          const uint32_t s = i % kBwStages, ph = (i / kBwStages) & 1;
-          mbar_wait(&empty[s], ph);
-          unsigned char* p = J.dy_base + (size_t)((k + i * J.pair_count) * kBwRows + r) * J.dy_pitch + rank * 256;
-          asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
-          asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + 128) : "memory");
+      // (1) X tiles by cp.async (LDGSTS): the TMA engine delivers ~40 B/clk per SM however the boxes are shaped (3.3 cycles per
+      //     128-byte box row), which bounds a dW pair at 0.85 us per 128-row stage against 0.54 us of MMAs; 128 threads copying
+      //     16-byte chunks straight into the SW128 slabs are a second path into SMEM that runs beside it.  Thread = one 16-byte
+      //     column chunk of the CTA's 256-byte half row, 16 rows per stage (rows tid/16 + 8 j).
+      // (2) Nobody reads a dY tile again once its MMAs have completed: drop this CTA's half of it (128 rows x 256 B) from L2
+      //     without a write-back (discard.global.L2), so that the hand-over costs no DRAM write either.
+      const int tid = (warp - 2) * 32 + lane;
+      const int ch = tid & 15, row0 = tid >> 4;                       // chunk in the half row (16 x 16 B), first row
+      const uint32_t full_leader0 = mapa_u32(smem_u32(&full[0]), 0);
+      auto discard_stage = [&](int i) {
+        unsigned char* p = J.dy_base + (size_t)((k + i * J.pair_count) * kBwRows + r) * J.dy_pitch + rank * 256;
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + 128) : "memory");
+      };
+      auto arrive_full = [&](int i) {                                  // this warp's chunks of stage i are in SMEM
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(full_leader0 + 8 * (uint32_t)(i % kBwStages));
+      };
+      for (int i = 0; i < n_my; ++i) {
+        const uint32_t s = i % kBwStages, ph = (i / kBwStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);                                  // the MMAs of stage i - 3 have completed: slot free,
+        if (J.dy_base && i >= kBwStages) discard_stage(i - kBwStages); // and its dY tile is dead
+        if (J.x_base) {
+          const unsigned char* g = J.x_base + (size_t)((k + i * J.pair_count) * kBwRows + row0) * J.x_pitch + rank * 256 + ch * 16;
+          const uint32_t dst = smem_u32(smem + s * kBwStage + (2 + (ch >> 3)) * kBwSlab);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int row = row0 + 8 * j;
+            const uint32_t a = dst + (uint32_t)(row >> 3) * 1024 + (uint32_t)(row & 7) * 128 + (((uint32_t)(ch & 7) ^ (uint32_t)(row & 7)) << 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(g + (size_t)(8 * j) * J.x_pitch) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (i >= 1) {                                                // two stages of copies in flight per thread
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            arrive_full(i - 1);
+          }
         }
       }
+      if (J.x_base) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        arrive_full(n_my - 1);
+      }
+      if (J.dy_base)
+        for (int i = max(0, n_my - kBwStages); i < n_my; ++i) {
+          mbar_wait(&empty[i % kBwStages], (i / kBwStages) & 1);
+          discard_stage(i);
+        }
       mbar_wait(done, 0);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
