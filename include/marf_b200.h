@@ -17,7 +17,7 @@
  *     caller (they are torch.Tensor.data_ptr()s in the Python host) unless marked "host";
  *   - all work is enqueued on the `stream` argument (a cudaStream_t passed as void*); no entry
  *     point synchronises the device or the stream except marf_create / marf_destroy and the three
- *     diagnostics that say so (marf_tc_selftest, marf_debug_read_bf16, marf_profile_read), so every
+ *     diagnostics that say so (marf_tc_selftest, marf_tf32_gemm, marf_debug_read_bf16, marf_profile_read), so every
  *     step / render / optimizer call can be captured into a CUDA graph;
  *   - every entry point returns 0 on success, else a marf_status / cudaError_t value;
  *     marf_last_error() returns a human-readable message for the last failure on that handle;
@@ -223,6 +223,15 @@ int marf_peer_allreduce(int device, int dtype, const void* const* peer_in, uint3
  * 3: out[N,K] = A[rows,N]^T aux[rows,K] (the dW kernel).  Synchronises `stream`.  Used by tests/ only. */
 int marf_tc_selftest(int device, int mode, int rows, int K, int N, const float* A, const float* W, const float* aux,
                      float* out, void* stream);
+
+/* diagnostic: run ONE 3xTF32 tensor-core GEMM of the precision=fp32 path (csrc/tc_tf32.cuh) on fp32 device arrays.
+ * mode 0: C[M,N] = epi(A[M,K] W[N,K]^T)   (forward layer; W row-major [N, ldw])
+ * mode 1: C[M,N] = epi(A[M,K] W[K,N])     (dX layer;      W row-major [K, ldw])
+ * mode 2: C[N,K] += A[M,N]^T W[M,K]       (dW layer;      W = the second activation matrix [M, ldw]; aux, if given, [N] += column sums of A)
+ * epi (modes 0/1) 0: + aux[N]; 1: relu(+ aux[N]); 2: plain; 3: zero where aux[M, ldaux] <= 0.
+ * M must be a multiple of 128, every ld a multiple of 4.  Synchronises `stream`.  Used by tests/ only. */
+int marf_tf32_gemm(marf_handle* h, int mode, int epi, int M, int N, int K, const float* A, int lda, const float* W, int ldw,
+                   float* C, int ldc, const float* aux, int ldaux, void* stream);
 
 /* diagnostic: fp32 copy of a resident bf16 buffer of the bf16 path's last chunk (which 0: input of `layer`, [rows, ld];
  * 1: gradient w.r.t. the output of `layer`, [rows, 256]).  Synchronises `stream`.  Used by tests/ and profiles/tools only. */

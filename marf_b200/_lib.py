@@ -19,7 +19,7 @@ EXPORTS = [
     "marf_abi_version", "marf_create", "marf_destroy", "marf_last_error", "marf_step", "marf_step_forward",
     "marf_step_backward", "marf_render", "marf_sl3_to_SL3", "marf_warp_corners", "marf_warp_points", "marf_compute_edges",
     "marf_launch_count", "marf_workspace_bytes", "marf_tc_selftest", "marf_adam_step", "marf_debug_read_bf16", "marf_profile", "marf_profile_read", "marf_loss_scalars", "marf_peer_allreduce",
-    "marf_forward_points",
+    "marf_forward_points", "marf_tf32_gemm",
 ]
 
 _i32, _u32, _i64, _f32, _f64, _vp = C.c_int32, C.c_uint32, C.c_int64, C.c_float, C.c_double, C.c_void_p
@@ -106,6 +106,9 @@ def load():
     lib.marf_compute_edges.restype = C.c_int
     lib.marf_tc_selftest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]
     lib.marf_tc_selftest.restype = C.c_int
+    lib.marf_tf32_gemm.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp,
+                                   C.c_int, _vp]
+    lib.marf_tf32_gemm.restype = C.c_int
     lib.marf_debug_read_bf16.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp, C.c_longlong, _vp]
     lib.marf_debug_read_bf16.restype = C.c_int
     lib.marf_profile.argtypes = [_vp, C.c_int]

@@ -6,6 +6,7 @@
 
 #include "engine.cuh"
 #include "fp32_kernels.cuh"
+#include "tc_tf32.cuh"
 
 using namespace marf;
 
@@ -90,6 +91,11 @@ static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_i
   for (int l = 0; l < n; ++l) {
     C.Wp[l] = wbase + off; C.gWp[l] = gbase + off; off += (size_t)C.ld_out[l] * C.ld_in[l];
     C.bp[l] = wbase + off; C.gbp[l] = gbase + off; off += C.ld_out[l];
+  }
+  for (int l = 0; l < n && h->fp32_tc && act_rows > 0; ++l) {
+    if (C.ld_out[l] < 32 || C.ld_in[l] < 32) continue;
+    C.Wt[l] = (float*)ws_alloc(h, (size_t)C.ld_in[l] * C.ld_out[l] * sizeof(float));
+    if (!C.Wt[l]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (transposed weights)");
   }
   for (int l = 0; l <= n; ++l) {
     int ld = l < n ? C.ld_in[l] : C.ld_out[n - 1];
@@ -188,6 +194,8 @@ extern "C" int marf_create(const marf_config* cfg, marf_handle** out) {
 
   marf_handle* h = new marf_handle();
   h->cfg = c;
+  h->n_sms = prop.multiProcessorCount;
+  h->fp32_tc = getenv("MARF_FP32_TC") ? atoi(getenv("MARF_FP32_TC")) != 0 : true;
   h->h = hh;
   h->w = ww;
   Geo& g = h->geo;
@@ -264,6 +272,106 @@ static int sgemm(marf_handle* h, cudaStream_t st, int M, int N, int K, const flo
   return MARF_OK;
 }
 
+// ---- 3xTF32 tensor-core GEMMs (tc_tf32.cuh)
+// C[M, N] = epi(A[M, K] * B[N, K]^T), B row-major [N, ldb]
+static long long* g_t32_trace = nullptr;      // diagnostics only (marf_tf32_gemm with MARF_T32_TRACE=1)
+
+template <int EPI>
+static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+                    int ldc, const float* aux, int ldaux) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, t32::kSmemBytes));
+    attr_set = true;
+  }
+  for (int n0 = 0; n0 < N; n0 += 256) {
+    t32::Params p{};
+    p.A = A; p.lda = lda;
+    p.B = B + (size_t)n0 * ldb; p.ldb = ldb;
+    p.C = C + n0; p.ldc = ldc;
+    p.aux = aux ? aux + n0 : nullptr; p.ldaux = ldaux;
+    p.M = M; p.K = K;
+    p.n_valid = std::min(256, N - n0);
+    p.trace = g_t32_trace;
+    launch_k(t32::k_tf32x3<t32::MODE_NT, EPI>, std::min(M / t32::kTileM, h->n_sms), t32::kThreads, t32::kSmemBytes, st, p);
+    LAUNCH_CHECK(h);
+  }
+  return MARF_OK;
+}
+
+// C[Np, Nq] += P[M, Np]^T * Q[M, Nq];  db[Np] += column sums of P (optional)
+static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, const float* P, int ldp, const float* Q, int ldq, float* C,
+                    int ldc, float* db) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_TN, t32::T_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     t32::kSmemBytes));
+    attr_set = true;
+  }
+  t32::Params p{};
+  p.A = P; p.lda = ldp; p.B = Q; p.ldb = ldq;
+  p.C = C; p.ldc = ldc;
+  p.db = db;
+  p.trace = g_t32_trace;
+  p.M = M;
+  p.p_valid = Np; p.n_valid = Nq;
+  dim3 grid(1, (Np + 127) / 128, (Nq + 255) / 256);
+  p.splits = std::max(1, std::min(M / t32::kStageK, h->n_sms / (int)(grid.y * grid.z)));
+  grid.x = p.splits;
+  launch_k(t32::k_tf32x3<t32::MODE_TN, t32::T_PLAIN>, grid, t32::kThreadsTN, t32::kSmemBytes, st, p);
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
+static bool tc_rows_ok(const marf_handle* h, int M) { return h->fp32_tc && M >= 128 && M % 128 == 0; }
+
+extern "C" int marf_tf32_gemm(marf_handle* h, int mode, int epi, int M, int N, int K, const float* A, int lda, const float* W, int ldw,
+                              float* C, int ldc, const float* aux, int ldaux, void* stream) {
+  if (!h || !A || !W || !C) return MARF_ERR_INVALID;
+  if (M < 128 || M % 128 || (lda | ldw | ldc | ldaux) % 4 || mode < 0 || mode > 2 || epi < 0 || epi > 3)
+    return fail(h, MARF_ERR_INVALID, "marf_tf32_gemm: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = MARF_OK;
+  float* wt = nullptr;
+  const bool trace = getenv("MARF_T32_TRACE") != nullptr;
+  if (trace) {
+    CUDA_TRY(h, cudaMalloc(&g_t32_trace, 512 * 8 * sizeof(long long)));
+    CUDA_TRY(h, cudaMemset(g_t32_trace, 0, 512 * 8 * sizeof(long long)));
+  }
+  if (mode == 2) {
+    rc = tgemm_tn(h, st, M, N, K, A, lda, W, ldw, C, ldc, const_cast<float*>(aux));
+  } else {
+    const float* B = W;
+    int ldb = ldw;
+    if (mode == 1) {           // W is [K, N]: the kernel wants B[N, K]
+      CUDA_TRY(h, cudaMalloc(&wt, (size_t)N * K * sizeof(float)));
+      launch_k(t32::k_tf32_transpose, dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st, W, K, N, ldw, wt, K);
+      B = wt;
+      ldb = K;
+    }
+    rc = epi == 0 ? tgemm_nt<t32::T_BIAS>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
+       : epi == 1 ? tgemm_nt<t32::T_BIAS_RELU>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
+       : epi == 2 ? tgemm_nt<t32::T_PLAIN>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
+                  : tgemm_nt<t32::T_RELU_MASK>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (trace && e == cudaSuccess) {
+    std::vector<long long> t(512 * 8);
+    cudaMemcpy(t.data(), g_t32_trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    const long long t0 = t[0];
+    fprintf(stderr, "# stage: loader[empty seen, stored, arrived] mma[full seen, committed]   (cycles since the first stamp)\n");
+    for (int i = 0; i < 40; ++i)
+      fprintf(stderr, "%3d: L %7lld %7lld %7lld   M %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 4] - t0,
+              t[i * 8 + 5] - t0);
+    fprintf(stderr, "# tile: epilogue[acc_full seen, released]\n");
+    for (int i = 0; i < 6; ++i) fprintf(stderr, "%3d: E %7lld %7lld\n", i, t[i * 8 + 6] - t0, t[i * 8 + 7] - t0);
+    cudaFree(g_t32_trace);
+    g_t32_trace = nullptr;
+  }
+  if (wt) cudaFree(wt);
+  if (e != cudaSuccess) return fail(h, MARF_ERR_CUDA, std::string("marf_tf32_gemm: ") + cudaGetErrorString(e));
+  return rc;
+}
+
 static int pick_split(int M, int N, int K) {
   long long tiles = (long long)((M + GBM - 1) / GBM) * ((N + (N <= 16 ? 15 : 127)) / (N <= 16 ? 16 : 128));
   int kt = (K + GBK - 1) / GBK;
@@ -280,6 +388,11 @@ static int pack_chain(marf_handle* h, cudaStream_t st, Chain& C, const float* co
     LAUNCH_CHECK(h);
     launch_k(k_pack, (C.ld_out[l] + 255) / 256, 256, 0, st, b[l], 1, C.k_out[l], C.bp[l], 1, C.ld_out[l]);
     LAUNCH_CHECK(h);
+    if (C.Wt[l]) {
+      launch_k(t32::k_tf32_transpose, dim3((C.ld_in[l] + 31) / 32, (C.ld_out[l] + 31) / 32), dim3(32, 8), 0, st, C.Wp[l], C.ld_out[l],
+               C.ld_in[l], C.ld_in[l], C.Wt[l], C.ld_out[l]);
+      LAUNCH_CHECK(h);
+    }
   }
   return MARF_OK;
 }
@@ -300,10 +413,16 @@ static int chain_forward(marf_handle* h, cudaStream_t st, Chain& C, int M) {
   for (int l = 0; l < C.n; ++l) {
     bool last = l == C.n - 1;
     int ldc = last ? C.ld_out[l] : C.ld_in[l + 1];
-    int rc = last ? sgemm<true, true, EPI_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l],
-                                                C.act[l + 1], ldc, C.bp[l], 0, 1)
-                  : sgemm<true, true, EPI_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l],
-                                                     C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0, 1);
+    int rc;
+    if (C.Wt[l] && tc_rows_ok(h, M))
+      rc = last ? tgemm_nt<t32::T_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0)
+                : tgemm_nt<t32::T_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1],
+                                             ldc, C.bp[l], 0);
+    else
+      rc = last ? sgemm<true, true, EPI_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l],
+                                              C.act[l + 1], ldc, C.bp[l], 0, 1)
+                : sgemm<true, true, EPI_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l],
+                                                   C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0, 1);
     if (rc) return rc;
     if (!last && (C.skip_mask & (1u << (l + 1)))) {
       long long tot = (long long)M * C.d_in;
@@ -323,7 +442,10 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
   for (int l = C.n - 1; l >= 0; --l) {
     int ldy = C.ld_out[l];
     int rc;
-    if (C.ld_out[l] <= 16) {
+    const bool tcl = C.Wt[l] && tc_rows_ok(h, M);
+    if (tcl) {
+      rc = tgemm_tn(h, st, M, C.ld_out[l], C.ld_in[l], cur, ldy, C.act[l], C.ld_in[l], C.gWp[l], C.ld_in[l], C.gbp[l]);
+    } else if (C.ld_out[l] <= 16) {
       rc = sgemm<false, false, EPI_ATOMIC_T>(h, st, C.ld_in[l], C.ld_out[l], M, C.act[l], C.ld_in[l], cur, ldy, C.gWp[l],
                                              C.ld_in[l], nullptr, 0, pick_split(C.ld_in[l], C.ld_out[l], M));
     } else {
@@ -331,7 +453,7 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
                                            C.ld_in[l], nullptr, 0, pick_split(C.ld_out[l], C.ld_in[l], M));
     }
     if (rc) return rc;
-    {
+    if (!tcl) {                 // (the tensor-core dW kernel sums the columns of dY while it splits them)
       int rpb = std::max(256, (M + 63) / 64);
       dim3 grid((C.ld_out[l] + 31) / 32, (M + rpb - 1) / rpb);
       launch_k(k_colsum, grid, 256, 0, st, M, C.ld_out[l], cur, ldy, C.gbp[l], rpb);
@@ -339,8 +461,9 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
     }
     if (l == 0 && !C.need_dx0) break;
     if (l == 0) {
-      rc = sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wp[0], C.ld_in[0], nxt, C.ld_in[0],
-                                         nullptr, 0, 1);
+      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wt[0], C.ld_out[0], nxt, C.ld_in[0], nullptr, 0)
+               : sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wp[0], C.ld_in[0], nxt, C.ld_in[0],
+                                               nullptr, 0, 1);
       if (rc) return rc;
       if (C.skip_mask) {
         long long tot = (long long)M * C.d_in;
@@ -348,8 +471,9 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
         LAUNCH_CHECK(h);
       }
     } else if (C.skip_mask & (1u << l)) {
-      rc = sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], h->dXscratch,
-                                         C.ld_in[l], nullptr, 0, 1);
+      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], h->dXscratch, C.ld_in[l], nullptr, 0)
+               : sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], h->dXscratch,
+                                               C.ld_in[l], nullptr, 0, 1);
       if (rc) return rc;
       long long tot = (long long)M * C.k_out[l - 1];
       launch_k(k_relu_mask, (unsigned)((tot + 255) / 256), 256, 0, st, M, C.k_out[l - 1], h->dXscratch, C.ld_in[l], C.act[l],
@@ -360,8 +484,10 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
                                                                  h->dX0acc, C.ld_in[0], 0, 1);
       LAUNCH_CHECK(h);
     } else {
-      rc = sgemm<true, false, EPI_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], nxt,
-                                             C.ld_in[l], C.act[l], C.ld_in[l], 1);
+      rc = tcl ? tgemm_nt<t32::T_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], C.act[l],
+                                            C.ld_in[l])
+               : sgemm<true, false, EPI_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], nxt,
+                                                   C.ld_in[l], C.act[l], C.ld_in[l], 1);
       if (rc) return rc;
     }
     std::swap(cur, nxt);

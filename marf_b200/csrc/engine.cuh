@@ -16,6 +16,9 @@ struct Chain {                 // one MLP in padded fp32 workspace form
   float* gbp[MARF_MAX_LAYERS];
   float* act[MARF_MAX_LAYERS + 1];  // act[l]: input of layer l [chunk, ld_in[l]]; act[n]: logits [chunk, ld_out[n-1]]
   bool need_dx0 = false;       // image MLP: yes (warp gradient); mask head: no
+  // 3xTF32 tensor-core path (tc_tf32.cuh): W^T [ld_in, ld_out] for the dX layers, rebuilt by pack_chain every step;
+  // nullptr for layers that stay on k_sgemm (N or K < 32)
+  float* Wt[MARF_MAX_LAYERS] = {};
   int max_ld = 0;
 };
 
@@ -49,6 +52,8 @@ struct marf_handle {
   bool feats_valid = false;    // mask-head input features cached in msk.act[0] (single chunk only)
   bool acts_valid = false;     // forward activations of the (single) chunk are resident for backward
   marf::Bf16State* bf16 = nullptr;
+  bool fp32_tc = true;         // precision=fp32: wide layers as 3xTF32 on the tensor cores (MARF_FP32_TC=0: CUDA-core SGEMMs only)
+  int n_sms = 148;
   int64_t launches = 0;
   int64_t ws_bytes = 0;
   // per-kernel-class timing (marf_profile): CUDA event pairs recorded on the launching stream around the tensor-core launches
