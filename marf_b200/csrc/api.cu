@@ -293,7 +293,8 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
     p.M = M; p.K = K;
     p.n_valid = std::min(256, N - n0);
     p.trace = g_t32_trace;
-    launch_k(t32::k_tf32x3<t32::MODE_NT, EPI>, std::min(M / t32::kTileM, h->n_sms), t32::kThreads, t32::kSmemBytes, st, p);
+    const int pairs = std::min((M / t32::kTileM + 1) / 2, h->n_sms / 2);
+    launch_k_cluster(t32::k_tf32x3<t32::MODE_NT, EPI>, 2 * pairs, t32::kThreads, t32::kSmemBytes, st, 2, p);
     LAUNCH_CHECK(h);
   }
   return MARF_OK;
@@ -315,10 +316,10 @@ static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, cons
   p.trace = g_t32_trace;
   p.M = M;
   p.p_valid = Np; p.n_valid = Nq;
-  dim3 grid(1, (Np + 127) / 128, (Nq + 255) / 256);
-  p.splits = std::max(1, std::min(M / t32::kStageK, h->n_sms / (int)(grid.y * grid.z)));
-  grid.x = p.splits;
-  launch_k(t32::k_tf32x3<t32::MODE_TN, t32::T_PLAIN>, grid, t32::kThreadsTN, t32::kSmemBytes, st, p);
+  dim3 grid(1, (Np + 255) / 256, (Nq + 255) / 256);
+  p.splits = std::max(1, std::min(M / t32::kStageK, h->n_sms / 2 / (int)(grid.y * grid.z)));
+  grid.x = 2 * p.splits;
+  launch_k_cluster(t32::k_tf32x3<t32::MODE_TN, t32::T_PLAIN>, grid, t32::kThreadsTN, t32::kSmemBytes, st, 2, p);
   LAUNCH_CHECK(h);
   return MARF_OK;
 }

@@ -16,9 +16,15 @@
 // halves the L2 -> SM bytes of a stage, which is what bounds the MODE_NT mainloop (every CTA re-reads the whole weight
 // matrix for every 128-row tile).
 //
-// Warp roles, MODE_NT (416 threads): warp 0 = MMA issuer (+ TMEM alloc), warps 1..8 = loaders, warps 9..12 = epilogue (warp
-// w owns TMEM lanes 32*(w%4)..+31); MODE_TN (384 threads): warps 0..7 = loaders, warps 8..11 = epilogue, lane 0 of warp 8
-// issues the MMAs first.  Two SMEM stages of 32 K-elements (A: 2 planes x 16 KB, B: 2 planes x 32 KB), two TMEM
+// The kernel runs on CTA pairs (clusters of 2, tcgen05 cta_group::2): one MMA is M = 256 (128 accumulator rows in each CTA's
+// TMEM) x N <= 256 with the B operand split across the pair (N/2 rows in each CTA's SMEM).  This is what makes the 3-term
+// product fit the SMEM bandwidth: a single-CTA M = 128 x N = 256 MMA re-reads 12 KB of SMEM per 128 cycles (96 of the 128
+// B/clk) and the loaders have to write another 96 KB per stage — measured 3,000 cycles per stage, 2x the MMA time; in the
+// pair each CTA reads 8 KB per MMA and writes 64 KB per stage, and the stages are small enough for a ring of three.
+//
+// Warp roles, MODE_NT (416 threads): warp 0 = MMA issuer (leader CTA; + TMEM alloc), warps 1..8 = loaders, warps 9..12 =
+// epilogue (warp w owns TMEM lanes 32*(w%4)..+31); MODE_TN (384 threads): warps 0..7 = loaders, warps 8..11 = epilogue, lane
+// 0 of warp 8 issues the MMAs first.  Three SMEM stages of 32 K-elements (A and B-half: 2 planes x 16 KB each), two TMEM
 // accumulators of 256 columns, one 4 KB staging block per epilogue warp (the accumulator rows are re-read transposed so that
 // global stores / mask loads are whole 128-byte lines).
 #pragma once
@@ -33,22 +39,24 @@ using namespace marf::tc;
 constexpr int kThreads = 416;             // MODE_NT
 constexpr int kThreadsTN = 384;           // MODE_TN: the MMA issuer is lane 0 of the first epilogue warp (the epilogue starts when the
                                           // MMAs are done), 12 warps leave 168 registers for the two register sets of the loaders
-constexpr int kTileM = 128;
-constexpr int kStageK = 32;              // tf32 elements per 128-byte swizzle row
-constexpr int kStages = 2;
-constexpr int kPlaneA = kTileM * 128;    // 16 KB
-constexpr int kPlaneB = 256 * 128;       // 32 KB
-constexpr int kStageBytes = 2 * kPlaneA + 2 * kPlaneB;   // 96 KB
-constexpr int kOutStage = 4 * 4096;      // epilogue staging, 4 KB per warp
+constexpr int kTileM = 128;               // accumulator rows per CTA (the pair's MMA is M = 256)
+constexpr int kStageK = 32;               // tf32 elements per 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kPlane = kTileM * 128;      // 16 KB: one [128 rows x 32] plane
+constexpr int kStageBytes = 4 * kPlane;   // A big, A small, B-half big, B-half small
+constexpr int kOutStage = 4 * 4096;       // epilogue staging, 4 KB per warp
 constexpr int kSmemBytes = kStages * kStageBytes + kOutStage + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
 
 enum { MODE_NT = 0, MODE_TN = 1 };
 enum { T_BIAS = 0, T_BIAS_RELU = 1, T_PLAIN = 2, T_RELU_MASK = 3 };
 
 struct Params {
-  // MODE_NT: C[M, 0..n_valid) = epi(A[M,K] * B[n_valid,K]^T);  A row-major [M, lda], B row-major [n_valid, ldb]
-  // MODE_TN: C[p0 + i, q0 + j] += sum_m A[m, p0 + i] * B[m, q0 + j];  A = P [M, lda], B = Q [M, ldb];
-  //          CTA y takes 128 columns of P, CTA z 256 columns of Q, CTA x a range of rows;  db[p0 + i] += sum_m P[m, p0 + i]
+  // MODE_NT: C[M, 0..n_valid) = epi(A[M,K] * B[n_valid,K]^T);  A row-major [M, lda], B row-major [n_valid, ldb];
+  //          pair i works on the 256-row super-tiles i, i + pairs, ...; CTA r of the pair owns rows r*128.. of a super-tile
+  //          and stages rows r*npad/2.. of B
+  // MODE_TN: C[p, q] += sum_m A[m, p] * B[m, q];  A = P [M, lda], B = Q [M, ldb];  db[p] += sum_m P[m, p];
+  //          pair y takes 256 columns of P (CTA r: 128 of them), pair z 256 columns of Q (CTA r stages half of them),
+  //          pair x a range of rows
   const float* A;
   int lda;
   const float* B;
@@ -62,7 +70,7 @@ struct Params {
   int K;                 // MODE_NT: contraction length
   int n_valid;           // MODE_NT: output columns (<= 256);  MODE_TN: columns of Q
   int p_valid;           // MODE_TN: columns of P
-  int splits;            // MODE_TN: CTAs along the rows
+  int splits;            // MODE_TN: pairs along the rows
   long long* trace;      // diagnostics (MARF_T32_TRACE): clock64() stamps of CTA 0, [stage or tile][8]; nullptr in production
 };
 
@@ -92,6 +100,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
   asm volatile(
       "{\n\t.reg .pred p;\n\t setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the same on a CTA pair: D[256 rows: 128 in each CTA's TMEM] (+)= A[128 rows from each CTA] * B[N/2 rows from each CTA]
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -132,76 +148,80 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
   uint8_t* sOut = smem + kStages * kStageBytes;
   float* sBias = reinterpret_cast<float*>(sOut + kOutStage);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + kOutStage + 1024);
-  uint64_t* full = bars;                    // [kStages]  8 loader-warp arrivals
-  uint64_t* empty = bars + kStages;         // [kStages]  MMAs of the stage retired
-  uint64_t* acc_full = bars + 2 * kStages;  // [2]
-  uint64_t* acc_empty = acc_full + 2;       // [2]
+  uint64_t* full = bars;                    // [kStages]  leader CTA: 16 loader-warp arrivals (8 local + 8 from the peer)
+  uint64_t* empty = bars + kStages;         // [kStages]  both CTAs: MMAs of the stage retired (multicast commit)
+  uint64_t* acc_full = bars + 2 * kStages;  // [2]        both CTAs (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;       // [2]        leader CTA: 8 epilogue-warp arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs)
+  const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
 
-  // ---- work of this CTA
-  //   MODE_NT: 128-row tiles bid, bid + grid, ... each over ceil(K / 32) stages
+  // ---- work of this pair
+  //   MODE_NT: 256-row super-tiles pair, pair + n_pairs, ... each over ceil(K / 32) stages
   //   MODE_TN: one accumulator; a contiguous range of the 32-row stages
   int n_tiles_my, st_begin = 0, st_count;
   if (MODE == MODE_NT) {
-    const int n_tiles = p.M / kTileM;
-    n_tiles_my = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_super = (p.M / kTileM + 1) / 2;
+    n_tiles_my = pair < n_super ? (n_super - pair + n_pairs - 1) / n_pairs : 0;
     st_count = (p.K + kStageK - 1) / kStageK;
   } else {
     const int st_total = p.M / kStageK;
     const int per = (st_total + p.splits - 1) / p.splits;
-    st_begin = (int)blockIdx.x * per;
+    st_begin = pair * per;
     st_count = max(0, min(per, st_total - st_begin));
     n_tiles_my = st_count > 0 ? 1 : 0;
   }
-  const int p0 = MODE == MODE_TN ? (int)blockIdx.y * 128 : 0;     // first column of P (= first row of C) of this CTA
-  const int q0 = MODE == MODE_TN ? (int)blockIdx.z * 256 : 0;     // first column of Q (= first column of C)
-  const int nv = MODE == MODE_TN ? min(256, p.n_valid - q0) : p.n_valid;      // valid accumulator columns
-  const int npad = (nv + 15) / 16 * 16;                                       // MMA N
-  const int pv = MODE == MODE_TN ? min(128, p.p_valid - p0) : 128;            // valid accumulator rows
+  const int nv = MODE == MODE_TN ? min(256, p.n_valid - (int)blockIdx.z * 256) : p.n_valid;   // valid accumulator columns
+  const int npad = (nv + 15) / 16 * 16;                                                       // MMA N
+  const int bh = npad / 2;                                   // B-operand rows staged by each CTA
+  const int p0 = MODE == MODE_TN ? (int)blockIdx.y * 256 + (int)rank * 128 : 0;   // first column of P (= row of C) of this CTA
+  const int q0 = MODE == MODE_TN ? (int)blockIdx.z * 256 : 0;                    // first column of Q (= column of C) of the pair
+  const int pv = MODE == MODE_TN ? max(0, min(128, p.p_valid - p0)) : 128;       // valid accumulator rows of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 16); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == kMmaWarp) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
+  pdl_wait();                                // everything below reads the previous kernels' output
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();                        // the peer's barriers must be initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();                                // everything below reads the previous kernels' output
+  const int n_it = n_tiles_my * st_count;    // stages of this pair
 
   if (warp == kMmaWarp) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = idesc_tf32(kTileM, npad);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = idesc_tf32(2 * kTileM, npad);
       uint32_t it = 0;
       for (int t = 0; t < n_tiles_my; ++t) {
         const uint32_t a = t & 1, aph = (t >> 1) & 1;
-        mbar_wait(&acc_empty[a], aph ^ 1);
+        mbar_wait_cluster(&acc_empty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * 256;
         for (int ks = 0; ks < st_count; ++ks, ++it) {
           const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait_cluster(&full[s], ph);
           tc_fence_after();
-          if (p.trace && blockIdx.x == 0 && it < 512) p.trace[it * 8 + 4] = clock64();
+          if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 512) p.trace[it * 8 + 4] = clock64();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
           const uint64_t da_big = smem_desc_sw128(sa, 16, 1024);
-          const uint64_t da_small = smem_desc_sw128(sa + kPlaneA, 16, 1024);
-          const uint64_t db_big = smem_desc_sw128(sa + 2 * kPlaneA, 16, 1024);
-          const uint64_t db_small = smem_desc_sw128(sa + 2 * kPlaneA + kPlaneB, 16, 1024);
+          const uint64_t da_small = smem_desc_sw128(sa + kPlane, 16, 1024);
+          const uint64_t db_big = smem_desc_sw128(sa + 2 * kPlane, 16, 1024);
+          const uint64_t db_small = smem_desc_sw128(sa + 3 * kPlane, 16, 1024);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {       // 4 K-steps of 8 tf32 (32 bytes) per stage; small terms first
-            umma_tf32(d_tmem, da_small + 2 * j, db_big + 2 * j, idesc, (ks | j) != 0);
-            umma_tf32(d_tmem, da_big + 2 * j, db_small + 2 * j, idesc, 1);
-            umma_tf32(d_tmem, da_big + 2 * j, db_big + 2 * j, idesc, 1);
+            umma_tf32_2sm(d_tmem, da_small + 2 * j, db_big + 2 * j, idesc, (ks | j) != 0);
+            umma_tf32_2sm(d_tmem, da_big + 2 * j, db_small + 2 * j, idesc, 1);
+            umma_tf32_2sm(d_tmem, da_big + 2 * j, db_big + 2 * j, idesc, 1);
           }
-          umma_commit(&empty[s]);
-          if (p.trace && blockIdx.x == 0 && it < 512) p.trace[it * 8 + 5] = clock64();
+          umma_commit_2sm(&empty[s]);
+          if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 512) p.trace[it * 8 + 5] = clock64();
         }
-        umma_commit(&acc_full[a]);
+        umma_commit_2sm(&acc_full[a]);
       }
     }
     __syncwarp();
@@ -211,54 +231,59 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
     const int lt = threadIdx.x - 32 * kLoaderWarp0;          // 0..255
     const int lw = lt >> 5;                   // loader warp 0..7
     // two register sets = the operands of two stages in flight: the loads of stage i + 2 are issued as soon as the registers
-    // of stage i have been written to SMEM (they do not wait for an SMEM slot), so the load latency is hidden behind two
-    // stages of MMA time
-    float4 va[12], vb[12];
-    const int n_it = n_tiles_my * st_count;   // stages of this CTA (MODE_TN: n_tiles_my = 1)
+    // of stage i have been written to SMEM (they do not wait for an SMEM slot)
+    float4 va[8], vb[8];
+    const uint32_t full_remote = mapa_u32(smem_u32(&full[0]), 0);      // the leader's full[] barriers
+    auto publish = [&](uint32_t s) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(full_remote + 8u * s);
+    };
     if (MODE == MODE_NT) {
-      // chunk (row0 + 32 j, kc): row0 = lt >> 3 (0..31), kc = lt & 7; j = 0..3 for A (128 rows), 0..7 for B (256 rows);
-      // 8 lanes read one 128-byte row segment, the SW128 offset of (row0 + 32 j, kc) is base + 4096 j
+      // chunk (row0 + 32 j, kc): row0 = lt >> 3 (0..31), kc = lt & 7; j = 0..3 for A (this CTA's 128 rows) and for B (this
+      // CTA's half of the operand rows); 8 lanes read one 128-byte row segment, SW128 offset of (row0 + 32 j, kc) = base + 4096 j
       const int row0 = lt >> 3, kc = lt & 7;
       const uint32_t base = (uint32_t)(row0 >> 3) * 1024u + (uint32_t)(row0 & 7) * 128u + (uint32_t)((kc ^ (row0 & 7)) << 4);
-      const float* gB = p.B + (size_t)row0 * p.ldb + kc * 4;
-      int nB = 0;                             // B chunks of this thread that lie inside the matrix (the rest is zero)
+      const float* gB = p.B + (size_t)((int)rank * bh + row0) * p.ldb + kc * 4;
+      int nB = 0, nBs = 0;                    // B chunks inside the matrix (the rest is zero) / read by the MMA (rows < bh)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) nB += row0 + 32 * j < nv ? 1 : 0;
-      const int nBs = (npad - row0 + 31) / 32;          // chunks that the MMA reads (rows < npad)
-      auto issue = [&](float4 (&v)[12], int i) {
+      for (int j = 0; j < 4; ++j) {
+        nB += (row0 + 32 * j < bh && (int)rank * bh + row0 + 32 * j < nv) ? 1 : 0;
+        nBs += row0 + 32 * j < bh ? 1 : 0;
+      }
+      auto issue = [&](float4 (&v)[8], int i) {
         if (i >= n_it) return;
         const int t = i / st_count, ks = i - t * st_count;
-        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+        const int row = ((pair + t * n_pairs) * 2 + (int)rank) * kTileM + row0;      // first of this thread's 4 rows of A
         const int k = ks * kStageK + kc * 4;
         const bool kin = k < p.K;
-        const float* gA = p.A + (size_t)(tile * kTileM + row0) * p.lda + k;
+        const bool ain = kin && row < p.M;                 // (the last super-tile may have no second half)
+        const float* gA = p.A + (size_t)row * p.lda + k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kin) v[j] = *reinterpret_cast<const float4*>(gA + (size_t)(32 * j) * p.lda);
+          if (ain) v[j] = *reinterpret_cast<const float4*>(gA + (size_t)(32 * j) * p.lda);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (kin && j < nB) v[4 + j] = *reinterpret_cast<const float4*>(gB + (size_t)(32 * j) * p.ldb + ks * kStageK);
         }
       };
-      auto stage = [&](float4 (&v)[12], int i) {
+      auto stage = [&](float4 (&v)[8], int i) {
         if (i >= n_it) return;
         const uint32_t s = (uint32_t)i % kStages, ph = ((uint32_t)i / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_cluster(&empty[s], ph ^ 1);
         const bool tr = p.trace && blockIdx.x == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
         uint8_t* sa = smem + s * kStageBytes + base;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_store4(sa + j * 4096, sa + kPlaneA + j * 4096, v[j]);
+        for (int j = 0; j < 4; ++j) split_store4(sa + j * 4096, sa + kPlane + j * 4096, v[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j < nBs) split_store4(sa + 2 * kPlaneA + j * 4096, sa + 2 * kPlaneA + kPlaneB + j * 4096, v[4 + j]);
+        for (int j = 0; j < 4; ++j)
+          if (j < nBs) split_store4(sa + 2 * kPlane + j * 4096, sa + 3 * kPlane + j * 4096, v[4 + j]);
         if (tr) p.trace[i * 8 + 1] = clock64();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        publish(s);
         if (tr) p.trace[i * 8 + 2] = clock64();
         issue(v, i + 2);
       };
@@ -270,26 +295,29 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       }
     } else {
       // thread -> row m of the stage and column chunk c4_0 (of 4 floats); unit j adds 8 chunks (32 columns): P for j < 4
-      // (128 columns), Q for j = 4..11 (256 columns).  Component i of a chunk goes to operand row 4 c4 + i, element m:
-      // SW128 offset = base[i] + 4096 j.  Within a warp m covers 16 values and c4 two (lane >> 4): rows 4 c4 + i of the two
-      // halves differ by 4 in their swizzle phase, so the 32 lanes hit 32 distinct banks; the loads are 16 x 32-byte sectors.
+      // (this CTA's 128 columns), Q for j = 4..7 (this CTA's half of the pair's columns).  Component c of a chunk goes to
+      // operand row 4 c4 + c, element m: SW128 offset = base[c] + 4096 j.  Within a warp m covers 16 values and c4 two
+      // (lane >> 4): rows 4 c4 + c of the two halves differ by 4 in their swizzle phase, so the 32 lanes hit 32 distinct
+      // banks; the loads are 16 x 32-byte sectors.
       const int m = (lw & 1) * 16 + (lane & 15);
       const int c4_0 = (lw >> 1) * 2 + (lane >> 4);      // 0..7
       uint32_t base[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) base[i] = sw128_off((uint32_t)(4 * c4_0 + i), (uint32_t)m);
+      for (int c = 0; c < 4; ++c) base[c] = sw128_off((uint32_t)(4 * c4_0 + c), (uint32_t)m);
+      const int qc0 = q0 + (int)rank * bh;               // first column of Q staged by this CTA
       const float* gP = p.A + (size_t)m * p.lda + p0 + 4 * c4_0;
-      const float* gQ = p.B + (size_t)m * p.ldb + q0 + 4 * c4_0;
-      int nP = 0, nQ = 0;                      // units inside the matrices
+      const float* gQ = p.B + (size_t)m * p.ldb + qc0 + 4 * c4_0;
+      int nP = 0, nQ = 0, nQs = 0;             // units inside the matrices / read by the MMA (operand rows < bh)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) nP += 4 * c4_0 + 32 * j < pv ? 1 : 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) nQ += 4 * c4_0 + 32 * j < nv ? 1 : 0;
-      const int nQs = (npad - 4 * c4_0 + 31) / 32;       // units that the MMA reads (operand rows < npad)
+      for (int j = 0; j < 4; ++j) {
+        nP += 4 * c4_0 + 32 * j < pv ? 1 : 0;
+        nQ += (4 * c4_0 + 32 * j < bh && qc0 + 4 * c4_0 + 32 * j < p.n_valid) ? 1 : 0;
+        nQs += 4 * c4_0 + 32 * j < bh ? 1 : 0;
+      }
       float colsum[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) colsum[i] = 0.f;
-      auto issue = [&](float4 (&v)[12], int i) {
+      auto issue = [&](float4 (&v)[8], int i) {
         if (i >= n_it) return;
         const size_t r = (size_t)(st_begin + i) * kStageK;
 #pragma unroll
@@ -298,36 +326,33 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
           if (j < nP) v[j] = *reinterpret_cast<const float4*>(gP + r * p.lda + 32 * j);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < 4; ++j) {
           v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (j < nQ) v[4 + j] = *reinterpret_cast<const float4*>(gQ + r * p.ldb + 32 * j);
         }
       };
-      auto stage = [&](float4 (&v)[12], int i) {
+      auto stage = [&](float4 (&v)[8], int i) {
         if (i >= n_it) return;
         const uint32_t s = (uint32_t)i % kStages, ph = ((uint32_t)i / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_cluster(&empty[s], ph ^ 1);
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
         uint8_t* sa = smem + s * kStageBytes;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
+        for (int j = 0; j < 8; ++j) {
           if (j >= 4 && j - 4 >= nQs) continue;
-          uint8_t* pl = sa + (j < 4 ? j * 4096 : 2 * kPlaneA + (j - 4) * 4096);
-          const uint32_t pstride = j < 4 ? kPlaneA : kPlaneB;
+          uint8_t* pl = sa + (j < 4 ? j * 4096 : 2 * kPlane + (j - 4) * 4096);
           const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float b = tf32_rna(x[c]);
             *reinterpret_cast<float*>(pl + base[c]) = b;
-            *reinterpret_cast<float*>(pl + pstride + base[c]) = tf32_rna(x[c] - b);
+            *reinterpret_cast<float*>(pl + kPlane + base[c]) = tf32_rna(x[c] - b);
             if (j < 4) colsum[j * 4 + c] += x[c];
           }
         }
         if (tr) p.trace[i * 8 + 1] = clock64();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
+        publish(s);
         if (tr) p.trace[i * 8 + 2] = clock64();
         issue(v, i + 2);
       };
@@ -350,34 +375,38 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue (4 warps per CTA)
     const int q = warp & 3;
     uint8_t* stg = sOut + q * 4096;            // this warp's [32 rows x 32 columns] staging block, 16-byte chunks swizzled by row
     if ((EPI == T_BIAS || EPI == T_BIAS_RELU) && MODE == MODE_NT) {
       for (int i = threadIdx.x - 32 * kEpiWarp0; i < 256; i += 128) sBias[i] = i < nv ? p.aux[i] : 0.f;
       named_bar_sync(1, 128);
     }
+    const uint32_t acc_empty_remote = mapa_u32(smem_u32(&acc_empty[0]), 0);
     const int n_groups = (npad + 31) / 32;
     const int rr = lane >> 3, ch = lane & 7;   // read-back: rows rr + 4 i, chunk ch -> 8 lanes cover one 128-byte line
+    auto tile_row0 = [&](int t) { return ((pair + t * n_pairs) * 2 + (int)rank) * kTileM; };
     // T_RELU_MASK: the mask (the layer input) does not depend on the accumulator: the 8 lines a thread needs for a column
     // group are requested one group ahead (the first ones before the accumulator is even complete)
     float4 mk[8];
     auto load_mask = [&](int t, int g) {
       if (EPI != T_RELU_MASK || MODE != MODE_NT || t >= n_tiles_my) return;
       const int col = g * 32 + ch * 4;
-      const size_t grow0 = (size_t)((int)blockIdx.x + t * (int)gridDim.x) * kTileM + q * 32 + rr;
+      const int grow0 = tile_row0(t) + q * 32 + rr;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        mk[i] = col < nv ? *reinterpret_cast<const float4*>(p.aux + (grow0 + 4 * i) * p.ldaux + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mk[i] = (col < nv && grow0 < p.M) ? *reinterpret_cast<const float4*>(p.aux + (size_t)(grow0 + 4 * i) * p.ldaux + col)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     load_mask(0, 0);
     for (int t = 0; t < n_tiles_my; ++t) {
       const uint32_t a = t & 1, aph = (t >> 1) & 1;
-      mbar_wait(&acc_full[a], aph);
+      mbar_wait_cluster(&acc_full[a], aph);
       tc_fence_after();
       const bool tre = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * kEpiWarp0 && t < 64;
       if (tre) p.trace[t * 8 + 6] = clock64();
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256;
+      const bool rows_in = MODE == MODE_TN || tile_row0(t) < p.M;
       uint32_t v[32];
       tmem_ld32(tbase, v);
       for (int g = 0; g < n_groups; ++g) {
@@ -395,13 +424,13 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         }
         if (g + 1 < n_groups) load_mask(t, g + 1); else load_mask(t + 1, 0);
         const int col = g * 32 + ch * 4;
-        if (col < nv) {
+        if (col < nv && rows_in) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = rr + 4 * i;          // row inside this warp's 32
             float4 y = *reinterpret_cast<const float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             if (MODE == MODE_NT) {
-              const size_t grow = (size_t)((int)blockIdx.x + t * (int)gridDim.x) * kTileM + q * 32 + row;
+              const size_t grow = (size_t)(tile_row0(t) + q * 32 + row);
               if (EPI == T_BIAS || EPI == T_BIAS_RELU) {
                 const float4 b = *reinterpret_cast<const float4*>(sBias + col);
                 y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
@@ -421,13 +450,13 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[a]);
+      if (lane == 0) mbar_arrive_cluster(acc_empty_remote + 8u * a);
       if (tre) p.trace[t * 8 + 7] = clock64();
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  cluster_sync_all();        // the peer may still signal this CTA's barriers / read its SMEM until here
+  if (warp == kMmaWarp) { tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 }
 
 }  // namespace t32

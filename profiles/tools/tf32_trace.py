@@ -1,7 +1,8 @@
 """clock64 trace of CTA 0 of one 3xTF32 GEMM (MARF_T32_TRACE=1): python profiles/tools/tf32_trace.py <mode> <epi>"""
 import ctypes as C
 import os, sys
-os.environ["MARF_T32_TRACE"] = "1"
+if len(sys.argv) < 4:
+    os.environ["MARF_T32_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
