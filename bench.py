@@ -490,7 +490,7 @@ def run_marf(args):
                 f = measure(args.workload, "fp32", args, ctx, max(2, min(args.steps, 3)), 1, e2e=False, kernels=False)
                 line["value_fp32"] = f["value"]
                 line["fp32"] = dict(value=f["value"], unit="pixel-samples/s", ms_per_step=f["ms_per_step"], steps=f["steps"],
-                                    what="the same workload with precision=fp32 (the <=1e-3 parity mode, CUDA-core SGEMMs), resident inputs")
+                                    what="the same workload with precision=fp32 (the <=1e-3 parity mode: 3xTF32 tensor-core GEMMs for the wide layers, fp32 activations), resident inputs")
             except Exception as ex:                      # never lose the headline line to an extra
                 line["fp32"] = dict(unavailable=repr(ex)[:200])
         for extra in ("config2", "config4", "config5"):

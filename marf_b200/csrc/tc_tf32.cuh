@@ -114,6 +114,15 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+// streaming accesses of the epilogue: every line is touched once, keep them out of L1
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void split_store4(uint8_t* big, uint8_t* small, const float4& v) {
   float4 b, s;
   b.x = tf32_rna(v.x); b.y = tf32_rna(v.y); b.z = tf32_rna(v.z); b.w = tf32_rna(v.w);
@@ -395,8 +404,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       const int grow0 = tile_row0(t) + q * 32 + rr;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        mk[i] = (col < nv && grow0 < p.M) ? *reinterpret_cast<const float4*>(p.aux + (size_t)(grow0 + 4 * i) * p.ldaux + col)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        mk[i] = (col < nv && grow0 < p.M) ? ldg_stream(p.aux + (size_t)(grow0 + 4 * i) * p.ldaux + col) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
     load_mask(0, 0);
     for (int t = 0; t < n_tiles_my; ++t) {
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
                 const uint32_t b4 = curbits >> (4 * i);
                 y.x = (b4 & 1u) ? y.x : 0.f; y.y = (b4 & 2u) ? y.y : 0.f; y.z = (b4 & 4u) ? y.z : 0.f; y.w = (b4 & 8u) ? y.w : 0.f;
               }
-              *reinterpret_cast<float4*>(p.C + grow * p.ldc + col) = y;
+              stg_stream(p.C + grow * p.ldc + col, y);
             } else {
               const int crow = q * 32 + row;
               if (crow < pv) red_add_v4(p.C + (size_t)(p0 + crow) * p.ldc + q0 + col, y.x, y.y, y.z, y.w);

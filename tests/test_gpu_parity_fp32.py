@@ -1,5 +1,6 @@
 """GPU parity (precision=fp32): the CUDA path through the C ABI vs the CPU oracle and vs the goldens made from
-the unmodified reference.  Tolerances (north_star): per-pixel RGB / mask outputs <= 1e-3 max-abs; here the fp32
+the unmodified reference.  The wide layers run as 3xTF32 GEMMs on the tensor cores (csrc/tc_tf32.cuh) under the SAME bounds
+as the CUDA-core SGEMMs, which stay covered by test_step_fp32_cuda_cores (MARF_FP32_TC=0).  Tolerances (north_star): per-pixel RGB / mask outputs <= 1e-3 max-abs; here the fp32
 path is held to 2e-5 on outputs and 1e-3 relative (to each tensor's max-abs) on gradients."""
 import numpy as np
 import pytest
@@ -97,6 +98,34 @@ def test_step_fp32(name):
     res2 = gpu_util.run_step(eng, cfg, params, images, it, progress, two_phase=True)
     _compare(name, res2, cfg, params, images, it, progress, g, grad_tol=tol)
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["small_mask_edges", "mid_mask_c2f", "implicit_edges", "wide512_L10"])
+def test_step_fp32_cuda_cores(name, monkeypatch):
+    """MARF_FP32_TC=0: every GEMM on k_sgemm (the reference implementation of the fp32 mode), same bounds."""
+    import gpu_util
+    monkeypatch.setenv("MARF_FP32_TC", "0")
+    cfg, params, images, it, progress, g = cases.build_case(name)
+    eng = gpu_util.make_engine(cfg, "fp32")
+    res = gpu_util.run_step(eng, cfg, params, images, it, progress)
+    tol = 1e-2 if (cfg.L_2D and cfg.L_2D >= 10) else GRAD_TOL
+    _compare(name, res, cfg, params, images, it, progress, g, grad_tol=tol)
+    eng.close()
+
+
+def test_fp32_tensor_core_and_cuda_core_paths_agree(monkeypatch):
+    """the two implementations of the fp32 mode on the same step: outputs within 1e-5, gradients within 2e-4 of the peak"""
+    import gpu_util
+    cfg, params, images, it, progress, g = cases.build_case("mid_mask_c2f")
+    out = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("MARF_FP32_TC", tc)
+        eng = gpu_util.make_engine(cfg, "fp32")
+        out[tc] = gpu_util.run_step(eng, cfg, params, images, it, progress)
+        eng.close()
+    assert (out["1"]["rgb_pred"] - out["0"]["rgb_pred"]).abs().max().item() <= 1e-5
+    for k, v in out["0"]["grads"].items():
+        cases.check_close(out["1"]["grads"][k], v, 2e-4, k)
 
 
 @pytest.mark.parametrize("name", ["small_mask_c2f", "mid_mask", "implicit"])
