@@ -323,6 +323,30 @@ static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, cons
   LAUNCH_CHECK(h);
   return MARF_OK;
 }
+// the narrow output layer as bandwidth-bound row kernels (fp32_kernels.cuh: k_out_forward / k_out_backward)
+static bool out_rows_ok(const marf_handle* h, const Chain& C, int l) {
+  return h->fp32_tc && C.ld_out[l] == 4 && C.ld_in[l] <= 512 && C.ld_in[l] % 4 == 0;
+}
+static int out_forward(marf_handle* h, cudaStream_t st, Chain& C, int l, int M) {
+  const int K = C.ld_in[l], kch = (K + 127) / 128, grid = std::min((M + 7) / 8, 8 * h->n_sms);
+#define MARF_OUT_FWD(KCH)                                                                                                       \
+  launch_k(k_out_forward<KCH>, grid, 256, 0, st, M, K, C.k_out[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.bp[l], C.act[l + 1], \
+           C.ld_out[l])
+  if (kch == 1) MARF_OUT_FWD(1); else if (kch == 2) MARF_OUT_FWD(2); else if (kch == 3) MARF_OUT_FWD(3); else MARF_OUT_FWD(4);
+#undef MARF_OUT_FWD
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
+static int out_backward(marf_handle* h, cudaStream_t st, Chain& C, int l, int M, const float* dY, float* dX) {
+  const int K = C.ld_in[l], kch = (K + 127) / 128, grid = std::min((M + 7) / 8, 4 * h->n_sms);
+#define MARF_OUT_BWD(KCH)                                                                                                        \
+  launch_k(k_out_backward<KCH>, grid, 256, 0, st, M, K, C.k_out[l], C.act[l], C.ld_in[l], dY, C.ld_out[l], C.Wp[l], C.ld_in[l], dX, \
+           C.ld_in[l], C.gWp[l], C.gbp[l])
+  if (kch == 1) MARF_OUT_BWD(1); else if (kch == 2) MARF_OUT_BWD(2); else if (kch == 3) MARF_OUT_BWD(3); else MARF_OUT_BWD(4);
+#undef MARF_OUT_BWD
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
 static bool tc_rows_ok(const marf_handle* h, int M) { return h->fp32_tc && M >= 128 && M % 128 == 0; }
 
 extern "C" int marf_tf32_gemm(marf_handle* h, int mode, int epi, int M, int N, int K, const float* A, int lda, const float* W, int ldw,
@@ -415,7 +439,9 @@ static int chain_forward(marf_handle* h, cudaStream_t st, Chain& C, int M) {
     bool last = l == C.n - 1;
     int ldc = last ? C.ld_out[l] : C.ld_in[l + 1];
     int rc;
-    if (C.Wt[l] && tc_rows_ok(h, M))
+    if (last && out_rows_ok(h, C, l)) {
+      rc = out_forward(h, st, C, l, M);
+    } else if (C.Wt[l] && tc_rows_ok(h, M))
       rc = last ? tgemm_nt<t32::T_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0)
                 : tgemm_nt<t32::T_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1],
                                              ldc, C.bp[l], 0);
@@ -444,6 +470,13 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
     int ldy = C.ld_out[l];
     int rc;
     const bool tcl = C.Wt[l] && tc_rows_ok(h, M);
+    if (l == C.n - 1 && l > 0 && out_rows_ok(h, C, l) && !(C.skip_mask & (1u << l))) {
+      // output layer: dW, db and the masked dX in one pass over the layer input
+      rc = out_backward(h, st, C, l, M, cur, nxt);
+      if (rc) return rc;
+      std::swap(cur, nxt);
+      continue;
+    }
     if (tcl) {
       rc = tgemm_tn(h, st, M, C.ld_out[l], C.ld_in[l], cur, ldy, C.act[l], C.ld_in[l], C.gWp[l], C.ld_in[l], C.gbp[l]);
     } else if (C.ld_out[l] <= 16) {

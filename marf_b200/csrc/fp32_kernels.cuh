@@ -531,6 +531,127 @@ static __global__ void k_relu_mask(int M, int cols, const float* __restrict__ dX
 }
 
 // ============================================================================================
+// the narrow output layer (3 colour / 1 mask logits) of the fp32 mode: bandwidth-bound row kernels instead of three
+// SGEMM-shaped launches (forward N = 3; backward dW [3, K] + db + dX = (dY W) masked by the layer input, one pass over X)
+// ============================================================================================
+// lane l of a warp holds the 16-byte chunks l, l + 32, ... (KCH of them) of a row of X; W rows live in SMEM
+template <int KCH>
+static __global__ void __launch_bounds__(256) k_out_forward(int M, int K, int n_out, const float* __restrict__ X, int ldx,
+                                                            const float* __restrict__ W, int ldw, const float* __restrict__ b,
+                                                            float* __restrict__ Y, int ldy) {
+  pdl_wait();
+  __shared__ __align__(16) float sW[4][KCH * 128];
+  for (int i = threadIdx.x; i < 4 * KCH * 128; i += 256) {
+    const int j = i / (KCH * 128), c = i - j * (KCH * 128);
+    sW[j][c] = (j < n_out && c < K) ? W[(size_t)j * ldw + c] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * 8;
+  for (int m = blockIdx.x * 8 + warp; m < M; m += nwarps) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < KCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < K) {
+        const float4 x = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(&sW[j][c]);
+          acc[j] = fmaf(x.x, w.x, fmaf(x.y, w.y, fmaf(x.z, w.z, fmaf(x.w, w.w, acc[j]))));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+      float4 y;
+      y.x = acc[0] + b[0];
+      y.y = n_out > 1 ? acc[1] + b[1] : 0.f;
+      y.z = n_out > 2 ? acc[2] + b[2] : 0.f;
+      y.w = n_out > 3 ? acc[3] + b[3] : 0.f;
+      *reinterpret_cast<float4*>(Y + (size_t)m * ldy) = y;
+    }
+  }
+}
+
+// dX[m, c] = X[m, c] > 0 ? sum_j dY[m, j] W[j, c] : 0;  gW[j, c] += sum_m dY[m, j] X[m, c];  gb[j] += sum_m dY[m, j]
+template <int KCH>
+static __global__ void __launch_bounds__(256) k_out_backward(int M, int K, int n_out, const float* __restrict__ X, int ldx,
+                                                             const float* __restrict__ dY, int ldy, const float* __restrict__ W,
+                                                             int ldw, float* __restrict__ dX, int lddx, float* __restrict__ gW,
+                                                             float* __restrict__ gb) {
+  pdl_wait();
+  __shared__ __align__(16) float sW[4][KCH * 128];
+  __shared__ float sAcc[4][KCH * 128];
+  __shared__ float sB[4];
+  for (int i = threadIdx.x; i < 4 * KCH * 128; i += 256) {
+    const int j = i / (KCH * 128), c = i - j * (KCH * 128);
+    sW[j][c] = (j < n_out && c < K) ? W[(size_t)j * ldw + c] : 0.f;
+    sAcc[j][c] = 0.f;
+  }
+  if (threadIdx.x < 4) sB[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = gridDim.x * 8;
+  float aw[4][KCH][4];
+  float ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < KCH; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) aw[j][i][e] = 0.f;
+  for (int m = blockIdx.x * 8 + warp; m < M; m += nwarps) {
+    const float4 d4 = *reinterpret_cast<const float4*>(dY + (size_t)m * ldy);      // (ldy = 4: the padded logits row)
+    const float d[4] = {d4.x, n_out > 1 ? d4.y : 0.f, n_out > 2 ? d4.z : 0.f, n_out > 3 ? d4.w : 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ab[j] += d[j];
+#pragma unroll
+    for (int i = 0; i < KCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      if (c < K) {
+        const float4 x = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + c);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+        float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(&sW[j][c]);
+          const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            g[e] = fmaf(d[j], wv[e], g[e]);
+            aw[j][i][e] = fmaf(d[j], xv[e], aw[j][i][e]);
+          }
+        }
+        float4 o;
+        o.x = xv[0] > 0.f ? g[0] : 0.f; o.y = xv[1] > 0.f ? g[1] : 0.f; o.z = xv[2] > 0.f ? g[2] : 0.f; o.w = xv[3] > 0.f ? g[3] : 0.f;
+        *reinterpret_cast<float4*>(dX + (size_t)m * lddx + c) = o;
+      }
+    }
+  }
+  // block reduction of the weight-gradient partials, then one atomic per entry and block
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < KCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (c < K) atomicAdd(&sAcc[j][c + e], aw[j][i][e]);
+    }
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(&sB[j], ab[j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_out * KCH * 128; i += 256) {
+    const int j = i / (KCH * 128), c = i - j * (KCH * 128);
+    if (c < K) atomicAdd(&gW[(size_t)j * ldw + c], sAcc[j][c]);
+  }
+  if (threadIdx.x < n_out) atomicAdd(&gb[threadIdx.x], sB[threadIdx.x]);
+}
+
+// ============================================================================================
 // losses (model/planar.py:355-391) — statistics pass and gradient pass
 // ============================================================================================
 struct LossArgs {
