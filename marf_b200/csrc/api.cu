@@ -96,6 +96,11 @@ static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_i
     if (C.ld_out[l] < 32 || C.ld_in[l] < 32) continue;
     C.Wt[l] = (float*)ws_alloc(h, (size_t)C.ld_in[l] * C.ld_out[l] * sizeof(float));
     if (!C.Wt[l]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (transposed weights)");
+    if (l + 1 < n && !(skip_mask & (1u << (l + 1)))) {      // sign bits of this layer's output = the input of layer l + 1
+      C.bits_ld[l + 1] = (C.ld_out[l] + 31) / 32;
+      C.bits[l + 1] = (uint32_t*)ws_alloc(h, (size_t)act_rows * C.bits_ld[l + 1] * sizeof(uint32_t));
+      if (!C.bits[l + 1]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (sign bits)");
+    }
   }
   for (int l = 0; l <= n; ++l) {
     int ld = l < n ? C.ld_in[l] : C.ld_out[n - 1];
@@ -278,7 +283,7 @@ static long long* g_t32_trace = nullptr;      // diagnostics only (marf_tf32_gem
 
 template <int EPI>
 static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-                    int ldc, const float* aux, int ldaux) {
+                    int ldc, const float* aux, int ldaux, uint32_t* bits = nullptr, int bits_ld = 0) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, t32::kSmemBytes));
@@ -292,6 +297,10 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
     p.aux = aux ? aux + n0 : nullptr; p.ldaux = ldaux;
     p.M = M; p.K = K;
     p.n_valid = std::min(256, N - n0);
+    if (bits) {
+      if (EPI == t32::T_RELU_BITS) p.bits_in = bits + n0 / 32; else p.bits_out = bits + n0 / 32;
+      p.bits_ld = bits_ld;
+    }
     p.trace = g_t32_trace;
     const int pairs = std::min((M / t32::kTileM + 1) / 2, h->n_sms / 2);
     launch_k_cluster(t32::k_tf32x3<t32::MODE_NT, EPI>, 2 * pairs, t32::kThreads, t32::kSmemBytes, st, 2, p);
@@ -439,13 +448,15 @@ static int chain_forward(marf_handle* h, cudaStream_t st, Chain& C, int M) {
     bool last = l == C.n - 1;
     int ldc = last ? C.ld_out[l] : C.ld_in[l + 1];
     int rc;
+    if (!last) C.bits_ok[l + 1] = false;
     if (last && out_rows_ok(h, C, l)) {
       rc = out_forward(h, st, C, l, M);
-    } else if (C.Wt[l] && tc_rows_ok(h, M))
+    } else if (C.Wt[l] && tc_rows_ok(h, M)) {
+      if (!last) C.bits_ok[l + 1] = C.bits[l + 1] != nullptr;
       rc = last ? tgemm_nt<t32::T_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0)
                 : tgemm_nt<t32::T_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1],
-                                             ldc, C.bp[l], 0);
-    else
+                                             ldc, C.bp[l], 0, C.bits[l + 1], C.bits_ld[l + 1]);
+    } else
       rc = last ? sgemm<true, true, EPI_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l],
                                               C.act[l + 1], ldc, C.bp[l], 0, 1)
                 : sgemm<true, true, EPI_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l],
@@ -518,7 +529,10 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
                                                                  h->dX0acc, C.ld_in[0], 0, 1);
       LAUNCH_CHECK(h);
     } else {
-      rc = tcl ? tgemm_nt<t32::T_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], C.act[l],
+      rc = tcl && C.bits_ok[l]
+               ? tgemm_nt<t32::T_RELU_BITS>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], nullptr, 0,
+                                            C.bits[l], C.bits_ld[l])
+           : tcl ? tgemm_nt<t32::T_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], C.act[l],
                                             C.ld_in[l])
                : sgemm<true, false, EPI_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], nxt,
                                                    C.ld_in[l], C.act[l], C.ld_in[l], 1);

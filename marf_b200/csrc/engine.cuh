@@ -19,6 +19,11 @@ struct Chain {                 // one MLP in padded fp32 workspace form
   // 3xTF32 tensor-core path (tc_tf32.cuh): W^T [ld_in, ld_out] for the dX layers, rebuilt by pack_chain every step;
   // nullptr for layers that stay on k_sgemm (N or K < 32)
   float* Wt[MARF_MAX_LAYERS] = {};
+  // sign bits of the input of layer l (= ReLU output of layer l - 1), [rows, bits_ld[l]] words, written by the tensor-core
+  // forward layer and read by the dX layer instead of the fp32 input; bits_ok[l]: written by the last forward of this chunk
+  uint32_t* bits[MARF_MAX_LAYERS] = {};
+  int bits_ld[MARF_MAX_LAYERS] = {};
+  bool bits_ok[MARF_MAX_LAYERS] = {};
   int max_ld = 0;
 };
 

@@ -48,7 +48,7 @@ constexpr int kOutStage = 4 * 4096;       // epilogue staging, 4 KB per warp
 constexpr int kSmemBytes = kStages * kStageBytes + kOutStage + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
 
 enum { MODE_NT = 0, MODE_TN = 1 };
-enum { T_BIAS = 0, T_BIAS_RELU = 1, T_PLAIN = 2, T_RELU_MASK = 3 };
+enum { T_BIAS = 0, T_BIAS_RELU = 1, T_PLAIN = 2, T_RELU_MASK = 3, T_RELU_BITS = 4 };
 
 struct Params {
   // MODE_NT: C[M, 0..n_valid) = epi(A[M,K] * B[n_valid,K]^T);  A row-major [M, lda], B row-major [n_valid, ldb];
@@ -66,6 +66,9 @@ struct Params {
   const float* aux;      // bias [N] (T_BIAS*), or the layer input [M, ldaux] (T_RELU_MASK)
   int ldaux;
   float* db;             // MODE_TN: column sums of P (nullptr: not wanted)
+  uint32_t* bits_out;    // T_BIAS_RELU: optional [M, bits_ld] words, bit c of word g of a row = (output column 32 g + c > 0)
+  const uint32_t* bits_in;   // T_RELU_BITS: the same layout, written by the forward layer that produced this layer's input
+  int bits_ld;           // words per row
   int M;                 // rows (multiple of 128)
   int K;                 // MODE_NT: contraction length
   int n_valid;           // MODE_NT: output columns (<= 256);  MODE_TN: columns of Q
@@ -123,12 +126,31 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
 __device__ __forceinline__ void stg_stream(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
-__device__ __forceinline__ void split_store4(uint8_t* big, uint8_t* small, const float4& v) {
+// explicit shared-space accesses (32-bit shared addresses): through the rounded-up dynamic-SMEM pointer the compiler only
+// sees generic pointers and emits ST.E / LD.E, which cost the loaders 2-3x the issue time of STS / LDS
+__device__ __forceinline__ void sts128(uint32_t a, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg128(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void split_store4(uint32_t big, uint32_t small, const float4& v) {
   float4 b, s;
   b.x = tf32_rna(v.x); b.y = tf32_rna(v.y); b.z = tf32_rna(v.z); b.w = tf32_rna(v.w);
   s.x = tf32_rna(v.x - b.x); s.y = tf32_rna(v.y - b.y); s.z = tf32_rna(v.z - b.z); s.w = tf32_rna(v.w - b.w);
-  *reinterpret_cast<float4*>(big) = b;
-  *reinterpret_cast<float4*>(small) = s;
+  sts128(big, b);
+  sts128(small, s);
 }
 
 // out[c][r] = in[r][c]  (the dX layers read W^T as a K-major operand)
@@ -271,12 +293,12 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ain) v[j] = *reinterpret_cast<const float4*>(gA + (size_t)(32 * j) * p.lda);
+          if (ain) v[j] = ldg128(gA + (size_t)(32 * j) * p.lda);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kin && j < nB) v[4 + j] = *reinterpret_cast<const float4*>(gB + (size_t)(32 * j) * p.ldb + ks * kStageK);
+          if (kin && j < nB) v[4 + j] = ldg128(gB + (size_t)(32 * j) * p.ldb + ks * kStageK);
         }
       };
       auto stage = [&](float4 (&v)[8], int i) {
@@ -285,7 +307,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         mbar_wait_cluster(&empty[s], ph ^ 1);
         const bool tr = p.trace && blockIdx.x == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
-        uint8_t* sa = smem + s * kStageBytes + base;
+        const uint32_t sa = smem_u32(smem) + s * kStageBytes + base;
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_store4(sa + j * 4096, sa + kPlane + j * 4096, v[j]);
 #pragma unroll
@@ -332,12 +354,12 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < nP) v[j] = *reinterpret_cast<const float4*>(gP + r * p.lda + 32 * j);
+          if (j < nP) v[j] = ldg128(gP + r * p.lda + 32 * j);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < nQ) v[4 + j] = *reinterpret_cast<const float4*>(gQ + r * p.ldb + 32 * j);
+          if (j < nQ) v[4 + j] = ldg128(gQ + r * p.ldb + 32 * j);
         }
       };
       auto stage = [&](float4 (&v)[8], int i) {
@@ -346,17 +368,17 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         mbar_wait_cluster(&empty[s], ph ^ 1);
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
-        uint8_t* sa = smem + s * kStageBytes;
+        const uint32_t sa = smem_u32(smem) + s * kStageBytes;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           if (j >= 4 && j - 4 >= nQs) continue;
-          uint8_t* pl = sa + (j < 4 ? j * 4096 : 2 * kPlane + (j - 4) * 4096);
+          const uint32_t pl = sa + (j < 4 ? j * 4096 : 2 * kPlane + (j - 4) * 4096);
           const float x[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const float b = tf32_rna(x[c]);
-            *reinterpret_cast<float*>(pl + base[c]) = b;
-            *reinterpret_cast<float*>(pl + kPlane + base[c]) = tf32_rna(x[c] - b);
+            sts32(pl + base[c], b);
+            sts32(pl + kPlane + base[c], tf32_rna(x[c] - b));
             if (j < 4) colsum[j * 4 + c] += x[c];
           }
         }
@@ -386,7 +408,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ epilogue (4 warps per CTA)
     const int q = warp & 3;
-    uint8_t* stg = sOut + q * 4096;            // this warp's [32 rows x 32 columns] staging block, 16-byte chunks swizzled by row
+    const uint32_t stg = smem_u32(sOut) + q * 4096;   // this warp's [32 rows x 32 columns] staging block, 16-byte chunks swizzled by row
     if ((EPI == T_BIAS || EPI == T_BIAS_RELU) && MODE == MODE_NT) {
       for (int i = threadIdx.x - 32 * kEpiWarp0; i < 256; i += 128) sBias[i] = i < nv ? p.aux[i] : 0.f;
       named_bar_sync(1, 128);
@@ -397,8 +419,14 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
     auto tile_row0 = [&](int t) { return ((pair + t * n_pairs) * 2 + (int)rank) * kTileM; };
     // T_RELU_MASK: the mask (the layer input) does not depend on the accumulator: the 8 lines a thread needs for a column
     // group are requested one group ahead (the first ones before the accumulator is even complete)
-    float4 mk[8];
+    float4 mk[EPI == T_RELU_MASK ? 8 : 1];
+    uint32_t mw[8];                            // T_RELU_BITS: the mask words of rows rr + 4 i
     auto load_mask = [&](int t, int g) {
+      if (EPI == T_RELU_BITS && MODE == MODE_NT && t < n_tiles_my) {
+        const int grow0 = tile_row0(t) + q * 32 + rr;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mw[i] = grow0 < p.M ? p.bits_in[(size_t)(grow0 + 4 * i) * p.bits_ld + g] : 0u;
+      }
       if (EPI != T_RELU_MASK || MODE != MODE_NT || t >= n_tiles_my) return;
       const int col = g * 32 + ch * 4;
       const int grow0 = tile_row0(t) + q * 32 + rr;
@@ -421,7 +449,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         tmem_ld_wait();
 #pragma unroll
         for (int c4 = 0; c4 < 8; ++c4)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((c4 ^ (lane & 7)) << 4)) = make_uint4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+          sts128u(stg + lane * 128 + ((c4 ^ (lane & 7)) << 4), v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
         if (g + 1 < n_groups) tmem_ld32(tbase + (g + 1) * 32, v);       // next group's accumulator columns travel meanwhile
         __syncwarp();
         uint32_t curbits = 0;                    // bit 4 i + c: element c of row rr + 4 i passes
@@ -429,21 +457,28 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             curbits |= ((mk[i].x > 0.f ? 1u : 0u) | (mk[i].y > 0.f ? 2u : 0u) | (mk[i].z > 0.f ? 4u : 0u) | (mk[i].w > 0.f ? 8u : 0u)) << (4 * i);
+        } else if (EPI == T_RELU_BITS) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) curbits |= ((mw[i] >> (4 * ch)) & 15u) << (4 * i);
         }
         if (g + 1 < n_groups) load_mask(t, g + 1); else load_mask(t + 1, 0);
         const int col = g * 32 + ch * 4;
+        uint32_t obits[8];                       // T_BIAS_RELU with bits_out: this thread's 4 sign bits of rows rr + 4 i
+#pragma unroll
+        for (int i = 0; i < 8; ++i) obits[i] = 0u;
         if (col < nv && rows_in) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int row = rr + 4 * i;          // row inside this warp's 32
-            float4 y = *reinterpret_cast<const float4*>(stg + row * 128 + ((ch ^ (row & 7)) << 4));
+            float4 y = lds128(stg + row * 128 + ((ch ^ (row & 7)) << 4));
             if (MODE == MODE_NT) {
               const size_t grow = (size_t)(tile_row0(t) + q * 32 + row);
               if (EPI == T_BIAS || EPI == T_BIAS_RELU) {
                 const float4 b = *reinterpret_cast<const float4*>(sBias + col);
                 y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
                 if (EPI == T_BIAS_RELU) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-              } else if (EPI == T_RELU_MASK) {
+                if (EPI == T_BIAS_RELU && p.bits_out) obits[i] = (y.x > 0.f ? 1u : 0u) | (y.y > 0.f ? 2u : 0u) | (y.z > 0.f ? 4u : 0u) | (y.w > 0.f ? 8u : 0u);
+              } else if (EPI == T_RELU_MASK || EPI == T_RELU_BITS) {
                 const uint32_t b4 = curbits >> (4 * i);
                 y.x = (b4 & 1u) ? y.x : 0.f; y.y = (b4 & 2u) ? y.y : 0.f; y.z = (b4 & 4u) ? y.z : 0.f; y.w = (b4 & 8u) ? y.w : 0.f;
               }
@@ -452,6 +487,17 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
               const int crow = q * 32 + row;
               if (crow < pv) red_add_v4(p.C + (size_t)(p0 + crow) * p.ldc + q0 + col, y.x, y.y, y.z, y.w);
             }
+          }
+        }
+        if (EPI == T_BIAS_RELU && MODE == MODE_NT && p.bits_out) {
+          // word of (row, g) = the 4-bit nibbles of the 8 lanes ch = 0..7 of that row
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t w = obits[i] << (4 * ch);
+            w |= __shfl_xor_sync(0xffffffffu, w, 1);
+            w |= __shfl_xor_sync(0xffffffffu, w, 2);
+            w |= __shfl_xor_sync(0xffffffffu, w, 4);
+            if (ch == 0 && rows_in && g < p.bits_ld) p.bits_out[(size_t)(tile_row0(t) + q * 32 + rr + 4 * i) * p.bits_ld + g] = w;
           }
         }
         __syncwarp();
