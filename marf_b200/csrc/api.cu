@@ -309,6 +309,28 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
   return MARF_OK;
 }
 
+// fp32 [rows, cols] tensor map, box [32 rows x 32 columns], SWIZZLE_128B, out-of-range columns read as zero
+static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    encode = (EncodeFn)fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (code " + std::to_string((int)r) + ")");
+  return MARF_OK;
+}
+
 // C[Np, Nq] += P[M, Np]^T * Q[M, Nq];  db[Np] += column sums of P (optional)
 static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, const float* P, int ldp, const float* Q, int ldq, float* C,
                     int ldc, float* db) {
@@ -323,6 +345,9 @@ static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, cons
   p.C = C; p.ldc = ldc;
   p.db = db;
   p.trace = g_t32_trace;
+  int rc = t32_tmap(h, &p.tmP, P, M, Np, ldp);
+  if (rc == MARF_OK) rc = t32_tmap(h, &p.tmQ, Q, M, Nq, ldq);
+  if (rc) return rc;
   p.M = M;
   p.p_valid = Np; p.n_valid = Nq;
   dim3 grid(1, (Np + 255) / 256, (Nq + 255) / 256);
@@ -394,8 +419,8 @@ extern "C" int marf_tf32_gemm(marf_handle* h, int mode, int epi, int M, int N, i
     const long long t0 = t[0];
     fprintf(stderr, "# stage: loader[empty seen, stored, arrived] mma[full seen, committed]   (cycles since the first stamp)\n");
     for (int i = 0; i < 40; ++i)
-      fprintf(stderr, "%3d: L %7lld %7lld %7lld   M %7lld %7lld\n", i, t[i * 8] - t0, t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 4] - t0,
-              t[i * 8 + 5] - t0);
+      fprintf(stderr, "%3d: L %7lld %7lld %7lld   M %7lld %7lld   (dW form: last loader warp %7lld, peer CTA %7lld)\n", i, t[i * 8] - t0,
+              t[i * 8 + 1] - t0, t[i * 8 + 2] - t0, t[i * 8 + 4] - t0, t[i * 8 + 5] - t0, t[i * 8 + 3] - t0, t[i * 8 + 6] - t0);
     fprintf(stderr, "# tile: epilogue[acc_full seen, released]\n");
     for (int i = 0; i < 6; ++i) fprintf(stderr, "%3d: E %7lld %7lld\n", i, t[i * 8 + 6] - t0, t[i * 8 + 7] - t0);
     cudaFree(g_t32_trace);

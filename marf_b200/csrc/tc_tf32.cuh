@@ -45,6 +45,12 @@ constexpr int kStages = 3;
 constexpr int kPlane = kTileM * 128;      // 16 KB: one [128 rows x 32] plane
 constexpr int kStageBytes = 4 * kPlane;   // A big, A small, B-half big, B-half small
 constexpr int kOutStage = 4 * 4096;       // epilogue staging, 4 KB per warp
+// MODE_TN: two plane stages + a ring of two raw stages: the [32 rows x 128 columns] tiles of P and of this CTA's half of Q as
+// they lie in memory, brought in by TMA as 4 + 4 boxes of [32 rows x 32 columns] (SWIZZLE_128B, so that the 8 consecutive rows
+// of one 16-byte column chunk a quarter-warp reads fall into 8 different bank groups)
+constexpr int kRawBox = kStageK * 128;               // 4 KB
+constexpr int kRawStage = 8 * kRawBox;               // 32 KB
+constexpr int kRawOff = 2 * kStageBytes;
 constexpr int kSmemBytes = kStages * kStageBytes + kOutStage + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
 
 enum { MODE_NT = 0, MODE_TN = 1 };
@@ -74,6 +80,7 @@ struct Params {
   int n_valid;           // MODE_NT: output columns (<= 256);  MODE_TN: columns of Q
   int p_valid;           // MODE_TN: columns of P
   int splits;            // MODE_TN: pairs along the rows
+  CUtensorMap tmP, tmQ;  // MODE_TN: fp32 [M rows, valid columns] maps of P and Q, box [32 x 32], SWIZZLE_128B, zero fill
   long long* trace;      // diagnostics (MARF_T32_TRACE): clock64() stamps of CTA 0, [stage or tile][8]; nullptr in production
 };
 
@@ -113,6 +120,14 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -183,7 +198,10 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
   uint64_t* empty = bars + kStages;         // [kStages]  both CTAs: MMAs of the stage retired (multicast commit)
   uint64_t* acc_full = bars + 2 * kStages;  // [2]        both CTAs (multicast commit)
   uint64_t* acc_empty = acc_full + 2;       // [2]        leader CTA: 8 epilogue-warp arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* raw_full = acc_empty + 2;       // [2]        MODE_TN: bytes of a raw stage landed
+  uint64_t* raw_empty = raw_full + 2;       // [2]        MODE_TN: 8 loader warps have read the raw stage
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 2);
+  constexpr int kSt = MODE == MODE_TN ? 2 : kStages;      // plane stages
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs)
   const int pair = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
@@ -212,7 +230,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 16); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); mbar_init(&raw_full[a], 1); mbar_init(&raw_empty[a], 8); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) { tmem_alloc_2sm(tmem_slot, 512); tmem_relinquish_2sm(); }
@@ -234,7 +252,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * 256;
         for (int ks = 0; ks < st_count; ++ks, ++it) {
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+          const uint32_t s = it % kSt, ph = (it / kSt) & 1;
           mbar_wait_cluster(&full[s], ph);
           tc_fence_after();
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 512) p.trace[it * 8 + 4] = clock64();
@@ -336,8 +354,6 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
 #pragma unroll
       for (int c = 0; c < 4; ++c) base[c] = sw128_off((uint32_t)(4 * c4_0 + c), (uint32_t)m);
       const int qc0 = q0 + (int)rank * bh;               // first column of Q staged by this CTA
-      const float* gP = p.A + (size_t)m * p.lda + p0 + 4 * c4_0;
-      const float* gQ = p.B + (size_t)m * p.ldb + qc0 + 4 * c4_0;
       int nP = 0, nQ = 0, nQs = 0;             // units inside the matrices / read by the MMA (operand rows < bh)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -348,23 +364,25 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       float colsum[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) colsum[i] = 0.f;
-      auto issue = [&](float4 (&v)[8], int i) {
-        if (i >= n_it) return;
-        const size_t r = (size_t)(st_begin + i) * kStageK;
+      const uint32_t raw0 = smem_u32(smem) + kRawOff + (uint32_t)m * 128u + (uint32_t)((c4_0 ^ (m & 7)) << 4);
+      for (int i = 0; i < n_it; ++i) {
+        // raw stage -> registers (conflict-free 16-byte reads), release the raw slot, then wait for a plane slot
+        const uint32_t rs = (uint32_t)i & 1u, rph = ((uint32_t)i >> 1) & 1u;
+        mbar_wait(&raw_full[rs], rph);
+        float4 v[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < nP) v[j] = ldg128(gP + r * p.lda + 32 * j);
+          if (j < nP) v[j] = lds128(raw0 + rs * kRawStage + j * kRawBox);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (j < nQ) v[4 + j] = ldg128(gQ + r * p.ldb + 32 * j);
+          if (j < nQ) v[4 + j] = lds128(raw0 + rs * kRawStage + (4 + j) * kRawBox);
         }
-      };
-      auto stage = [&](float4 (&v)[8], int i) {
-        if (i >= n_it) return;
-        const uint32_t s = (uint32_t)i % kStages, ph = ((uint32_t)i / kStages) & 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        const uint32_t s = (uint32_t)i % kSt, ph = ((uint32_t)i / kSt) & 1;
         mbar_wait_cluster(&empty[s], ph ^ 1);
         const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
@@ -385,13 +403,8 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         if (tr) p.trace[i * 8 + 1] = clock64();
         publish(s);
         if (tr) p.trace[i * 8 + 2] = clock64();
-        issue(v, i + 2);
-      };
-      issue(va, 0);
-      issue(vb, 1);
-      for (int i = 0; i < n_it; i += 2) {
-        stage(va, i);
-        stage(vb, i + 1);
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && lt == 224 && i < 512) p.trace[i * 8 + 3] = clock64();   // last loader warp
+        if (p.trace && blockIdx.x == 1 && blockIdx.y == 0 && lt == 0 && i < 512) p.trace[i * 8 + 6] = clock64();     // peer CTA
       }
       if (p.db && blockIdx.z == 0 && st_count > 0) {
         // column sums of P: reduce over the 16 rows m of this warp (lane bits 0..3), one atomic per column and warp
@@ -406,6 +419,25 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       }
     }
   } else if (warp >= kEpiWarp0) {
+    if (MODE == MODE_TN && warp == kEpiWarp0 + 1 && lane == 0) {
+      // ---------------------------------------------------------------- raw-stage producer (MODE_TN): 8 TMA boxes per stage.
+      // (row-wise cp.async.bulk copies — 64 per stage — cost the copy engine ~65 cycles each: 4,200 cycles per stage)
+      const int qc0 = q0 + (int)rank * bh;
+      prefetch_tmap(&p.tmP);
+      prefetch_tmap(&p.tmQ);
+      for (int i = 0; i < n_it; ++i) {
+        const uint32_t rs = (uint32_t)i & 1u, rph = ((uint32_t)i >> 1) & 1u;
+        mbar_wait(&raw_empty[rs], rph ^ 1);
+        mbar_expect_tx(&raw_full[rs], kRawStage);
+        uint8_t* dst = smem + kRawOff + rs * kRawStage;
+        const int r0 = (st_begin + i) * kStageK;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(dst + j * kRawBox, &p.tmP, p0 + 32 * j, r0, &raw_full[rs]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tma_load_2d(dst + (4 + j) * kRawBox, &p.tmQ, qc0 + 32 * j, r0, &raw_full[rs]);
+      }
+    }
+    __syncwarp();
     // ------------------------------------------------------------------ epilogue (4 warps per CTA)
     const int q = warp & 3;
     const uint32_t stg = smem_u32(sOut) + q * 4096;   // this warp's [32 rows x 32 columns] staging block, 16-byte chunks swizzled by row
