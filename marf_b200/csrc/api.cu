@@ -279,6 +279,28 @@ static int sgemm(marf_handle* h, cudaStream_t st, int M, int N, int K, const flo
 
 // ---- 3xTF32 tensor-core GEMMs (tc_tf32.cuh)
 // C[M, N] = epi(A[M, K] * B[N, K]^T), B row-major [N, ldb]
+// fp32 [rows, cols] tensor map, box [32 rows x 32 columns], SWIZZLE_128B, out-of-range columns read as zero
+static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    encode = (EncodeFn)fn;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (code " + std::to_string((int)r) + ")");
+  return MARF_OK;
+}
+
 static long long* g_t32_trace = nullptr;      // diagnostics only (marf_tf32_gemm with MARF_T32_TRACE=1)
 
 template <int EPI>
@@ -302,32 +324,14 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
       p.bits_ld = bits_ld;
     }
     p.trace = g_t32_trace;
+    if (EPI != t32::T_RELU_MASK) {
+      int rc = t32_tmap(h, &p.tmC, C + n0, M, p.n_valid, ldc);
+      if (rc) return rc;
+    }
     const int pairs = std::min((M / t32::kTileM + 1) / 2, h->n_sms / 2);
     launch_k_cluster(t32::k_tf32x3<t32::MODE_NT, EPI>, 2 * pairs, t32::kThreads, t32::kSmemBytes, st, 2, p);
     LAUNCH_CHECK(h);
   }
-  return MARF_OK;
-}
-
-// fp32 [rows, cols] tensor map, box [32 rows x 32 columns], SWIZZLE_128B, out-of-range columns read as zero
-static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows, int cols, int ld) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
-      return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    encode = (EncodeFn)fn;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(h, MARF_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (code " + std::to_string((int)r) + ")");
   return MARF_OK;
 }
 

@@ -44,7 +44,7 @@ constexpr int kStageK = 32;               // tf32 elements per 128-byte swizzle 
 constexpr int kStages = 3;
 constexpr int kPlane = kTileM * 128;      // 16 KB: one [128 rows x 32] plane
 constexpr int kStageBytes = 4 * kPlane;   // A big, A small, B-half big, B-half small
-constexpr int kOutStage = 4 * 4096;       // epilogue staging, 4 KB per warp
+constexpr int kOutStage = 8 * 4096;       // epilogue staging: two [32 rows x 32 columns] blocks per warp
 // MODE_TN: two plane stages + a ring of two raw stages: the [32 rows x 128 columns] tiles of P and of this CTA's half of Q as
 // they lie in memory, brought in by TMA as 4 + 4 boxes of [32 rows x 32 columns] (SWIZZLE_128B, so that the 8 consecutive rows
 // of one 16-byte column chunk a quarter-warp reads fall into 8 different bank groups)
@@ -80,6 +80,7 @@ struct Params {
   int n_valid;           // MODE_NT: output columns (<= 256);  MODE_TN: columns of Q
   int p_valid;           // MODE_TN: columns of P
   int splits;            // MODE_TN: pairs along the rows
+  CUtensorMap tmC;       // MODE_NT: fp32 [M rows, n_valid columns] map of C, box [32 x 32], SWIZZLE_128B (TMA stores clip)
   CUtensorMap tmP, tmQ;  // MODE_TN: fp32 [M rows, valid columns] maps of P and Q, box [32 x 32], SWIZZLE_128B, zero fill
   long long* trace;      // diagnostics (MARF_T32_TRACE): clock64() stamps of CTA 0, [stage or tile][8]; nullptr in production
 };
@@ -447,8 +448,75 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
     }
     const uint32_t acc_empty_remote = mapa_u32(smem_u32(&acc_empty[0]), 0);
     const int n_groups = (npad + 31) / 32;
-    const int rr = lane >> 3, ch = lane & 7;   // read-back: rows rr + 4 i, chunk ch -> 8 lanes cover one 128-byte line
     auto tile_row0 = [&](int t) { return ((pair + t * n_pairs) * 2 + (int)rank) * kTileM; };
+    constexpr bool kDirect = MODE == MODE_NT && EPI != T_RELU_MASK;
+    if (kDirect) {
+      // Thread = accumulator row: bias / ReLU / sign bits / bit mask are applied on the TMEM row layout, the [32 x 32] block of the
+      // warp goes to a swizzled staging buffer and from there to global memory by one TMA store (two buffers per warp: the store
+      // of a column group drains while the next one is prepared).  No read-back, no per-thread global stores.
+      uint8_t* buf_ptr = sOut + q * 8192;
+      const uint32_t buf0 = smem_u32(buf_ptr);
+      uint32_t n_buf = 0;
+      auto load_word = [&](int t, int g) -> uint32_t {
+        if (EPI != T_RELU_BITS || t >= n_tiles_my) return 0u;
+        const int row = tile_row0(t) + q * 32 + lane;
+        return row < p.M ? p.bits_in[(size_t)row * p.bits_ld + g] : 0u;
+      };
+      uint32_t wnext = load_word(0, 0);
+      if (lane == 0) prefetch_tmap(&p.tmC);
+      for (int t = 0; t < n_tiles_my; ++t) {
+        const uint32_t a = t & 1, aph = (t >> 1) & 1;
+        mbar_wait_cluster(&acc_full[a], aph);
+        tc_fence_after();
+        const bool tre = p.trace && blockIdx.x == 0 && threadIdx.x == 32 * kEpiWarp0 && t < 64;
+        if (tre) p.trace[t * 8 + 6] = clock64();
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256;
+        const int row0 = tile_row0(t) + q * 32;
+        const bool rows_in = row0 < p.M;
+        uint32_t v[32];
+        tmem_ld32(tbase, v);
+        for (int g = 0; g < n_groups; ++g, ++n_buf) {
+          const uint32_t boff = (n_buf & 1u) * 4096u;
+          if (lane == 0 && n_buf >= 2) bulk_wait_read<1>();        // the store that read this buffer two groups ago is done
+          __syncwarp();
+          const uint32_t w = wnext;
+          wnext = g + 1 < n_groups ? load_word(t, g + 1) : load_word(t + 1, 0);
+          tmem_ld_wait();
+          uint32_t ob = 0;
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {
+            float4 y = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
+                                   __uint_as_float(v[c4 * 4 + 3]));
+            if (EPI == T_BIAS || EPI == T_BIAS_RELU) {
+              const float4 b = *reinterpret_cast<const float4*>(sBias + g * 32 + c4 * 4);
+              y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
+              if (EPI == T_BIAS_RELU) {
+                y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
+                ob |= ((y.x > 0.f ? 1u : 0u) | (y.y > 0.f ? 2u : 0u) | (y.z > 0.f ? 4u : 0u) | (y.w > 0.f ? 8u : 0u)) << (4 * c4);
+              }
+            } else if (EPI == T_RELU_BITS) {
+              const uint32_t b4 = w >> (4 * c4);
+              y.x = (b4 & 1u) ? y.x : 0.f; y.y = (b4 & 2u) ? y.y : 0.f; y.z = (b4 & 4u) ? y.z : 0.f; y.w = (b4 & 8u) ? y.w : 0.f;
+            }
+            sts128(buf0 + boff + lane * 128 + ((c4 ^ (lane & 7)) << 4), y);
+          }
+          if (g + 1 < n_groups) tmem_ld32(tbase + (g + 1) * 32, v);     // next group's accumulator columns travel meanwhile
+          if (EPI == T_BIAS_RELU && p.bits_out && rows_in && g < p.bits_ld) p.bits_out[(size_t)(row0 + lane) * p.bits_ld + g] = ob;
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_in) {
+            tma_store_2d(&p.tmC, g * 32, row0, buf_ptr + boff);
+            bulk_commit();
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_remote + 8u * a);
+        if (tre) p.trace[t * 8 + 7] = clock64();
+      }
+      if (lane == 0) bulk_wait<0>();
+    } else {
+    const int rr = lane >> 3, ch = lane & 7;   // read-back: rows rr + 4 i, chunk ch -> 8 lanes cover one 128-byte line
     // T_RELU_MASK: the mask (the layer input) does not depend on the accumulator: the 8 lines a thread needs for a column
     // group are requested one group ahead (the first ones before the accumulator is even complete)
     float4 mk[EPI == T_RELU_MASK ? 8 : 1];
@@ -538,6 +606,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc_empty_remote + 8u * a);
       if (tre) p.trace[t * 8 + 7] = clock64();
+    }
     }
   }
   tc_fence_before();
