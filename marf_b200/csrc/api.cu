@@ -63,6 +63,9 @@ void set_schedule(marf_handle* h, float progress) {
 }  // namespace marf
 
 // ------------------------------------------------------------------------------------------------
+// 3xTF32 path: floats of the split form of an [N, K] weight operand (big planes + small planes, rows padded to 16, K to 32)
+static size_t t32_split_floats(int N, int K) { return (size_t)2 * round_up(N, 16) * round_up(K, 32); }
+
 static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_in0, uint32_t skip_mask, int d_in,
                        bool need_dx0, int act_rows) {
   C.n = n;
@@ -94,8 +97,9 @@ static int build_chain(marf_handle* h, Chain& C, int n, const int* outs, int k_i
   }
   for (int l = 0; l < n && h->fp32_tc && act_rows > 0; ++l) {
     if (C.ld_out[l] < 32 || C.ld_in[l] < 32) continue;
-    C.Wt[l] = (float*)ws_alloc(h, (size_t)C.ld_in[l] * C.ld_out[l] * sizeof(float));
-    if (!C.Wt[l]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (transposed weights)");
+    C.Wsp_f[l] = (float*)ws_alloc(h, t32_split_floats(C.ld_out[l], C.ld_in[l]) * sizeof(float));
+    C.Wt[l] = (float*)ws_alloc(h, t32_split_floats(C.ld_in[l], C.ld_out[l]) * sizeof(float));
+    if (!C.Wsp_f[l] || !C.Wt[l]) return fail(h, MARF_ERR_CUDA, "workspace allocation failed (split weights)");
     if (l + 1 < n && !(skip_mask & (1u << (l + 1)))) {      // sign bits of this layer's output = the input of layer l + 1
       C.bits_ld[l + 1] = (C.ld_out[l] + 31) / 32;
       C.bits[l + 1] = (uint32_t*)ws_alloc(h, (size_t)act_rows * C.bits_ld[l + 1] * sizeof(uint32_t));
@@ -280,7 +284,7 @@ static int sgemm(marf_handle* h, cudaStream_t st, int M, int N, int K, const flo
 // ---- 3xTF32 tensor-core GEMMs (tc_tf32.cuh)
 // C[M, N] = epi(A[M, K] * B[N, K]^T), B row-major [N, ldb]
 // fp32 [rows, cols] tensor map, box [32 rows x 32 columns], SWIZZLE_128B, out-of-range columns read as zero
-static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows, int cols, int ld) {
+static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows, int cols, int ld, int box_rows = 32) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   static EncodeFn encode = nullptr;
@@ -293,7 +297,7 @@ static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows,
   }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, 32};
+  cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -303,9 +307,20 @@ static int t32_tmap(marf_handle* h, CUtensorMap* m, const float* base, int rows,
 
 static long long* g_t32_trace = nullptr;      // diagnostics only (marf_tf32_gemm with MARF_T32_TRACE=1)
 
+// weights -> split planes (k_tf32_split_w)
+template <int TRANS>
+static int tf32_split(marf_handle* h, cudaStream_t st, const float* W, int ldw, int N, int K, float* out) {
+  const int nr = (int)round_up(N, 16), kpad = (int)round_up(K, 32);
+  launch_k(t32::k_tf32_split_w<TRANS>, (nr * kpad + 255) / 256, 256, 0, st, W, ldw, N, K, out, nr, kpad);
+  LAUNCH_CHECK(h);
+  return MARF_OK;
+}
+
+// C[M, N] = epi(A[M, K] * B[N, K]^T), B given in split form (tf32_split)
 template <int EPI>
-static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* Bsp, float* C,
                     int ldc, const float* aux, int ldaux, uint32_t* bits = nullptr, int bits_ld = 0) {
+  const int nr = (int)round_up(N, 16), kpad = (int)round_up(K, 32);
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, t32::kSmemBytes));
@@ -314,7 +329,6 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
   for (int n0 = 0; n0 < N; n0 += 256) {
     t32::Params p{};
     p.A = A; p.lda = lda;
-    p.B = B + (size_t)n0 * ldb; p.ldb = ldb;
     p.C = C + n0; p.ldc = ldc;
     p.aux = aux ? aux + n0 : nullptr; p.ldaux = ldaux;
     p.M = M; p.K = K;
@@ -324,10 +338,11 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
       p.bits_ld = bits_ld;
     }
     p.trace = g_t32_trace;
-    if (EPI != t32::T_RELU_MASK) {
-      int rc = t32_tmap(h, &p.tmC, C + n0, M, p.n_valid, ldc);
-      if (rc) return rc;
-    }
+    p.b_row0 = n0;
+    p.b_small = nr;
+    int rc = t32_tmap(h, &p.tmB, Bsp, 2 * nr, kpad, kpad, (int)round_up(p.n_valid, 16) / 2);
+    if (rc == MARF_OK && EPI != t32::T_RELU_MASK) rc = t32_tmap(h, &p.tmC, C + n0, M, p.n_valid, ldc);
+    if (rc) return rc;
     const int pairs = std::min((M / t32::kTileM + 1) / 2, h->n_sms / 2);
     launch_k_cluster(t32::k_tf32x3<t32::MODE_NT, EPI>, 2 * pairs, t32::kThreads, t32::kSmemBytes, st, 2, p);
     LAUNCH_CHECK(h);
@@ -403,18 +418,13 @@ extern "C" int marf_tf32_gemm(marf_handle* h, int mode, int epi, int M, int N, i
   if (mode == 2) {
     rc = tgemm_tn(h, st, M, N, K, A, lda, W, ldw, C, ldc, const_cast<float*>(aux));
   } else {
-    const float* B = W;
-    int ldb = ldw;
-    if (mode == 1) {           // W is [K, N]: the kernel wants B[N, K]
-      CUDA_TRY(h, cudaMalloc(&wt, (size_t)N * K * sizeof(float)));
-      launch_k(t32::k_tf32_transpose, dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st, W, K, N, ldw, wt, K);
-      B = wt;
-      ldb = K;
-    }
-    rc = epi == 0 ? tgemm_nt<t32::T_BIAS>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
-       : epi == 1 ? tgemm_nt<t32::T_BIAS_RELU>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
-       : epi == 2 ? tgemm_nt<t32::T_PLAIN>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux)
-                  : tgemm_nt<t32::T_RELU_MASK>(h, st, M, N, K, A, lda, B, ldb, C, ldc, aux, ldaux);
+    CUDA_TRY(h, cudaMalloc(&wt, t32_split_floats(N, K) * sizeof(float)));
+    rc = mode == 0 ? tf32_split<0>(h, st, W, ldw, N, K, wt) : tf32_split<1>(h, st, W, ldw, N, K, wt);
+    if (rc == MARF_OK)
+      rc = epi == 0 ? tgemm_nt<t32::T_BIAS>(h, st, M, N, K, A, lda, wt, C, ldc, aux, ldaux)
+         : epi == 1 ? tgemm_nt<t32::T_BIAS_RELU>(h, st, M, N, K, A, lda, wt, C, ldc, aux, ldaux)
+         : epi == 2 ? tgemm_nt<t32::T_PLAIN>(h, st, M, N, K, A, lda, wt, C, ldc, aux, ldaux)
+                    : tgemm_nt<t32::T_RELU_MASK>(h, st, M, N, K, A, lda, wt, C, ldc, aux, ldaux);
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (trace && e == cudaSuccess) {
@@ -452,9 +462,9 @@ static int pack_chain(marf_handle* h, cudaStream_t st, Chain& C, const float* co
     launch_k(k_pack, (C.ld_out[l] + 255) / 256, 256, 0, st, b[l], 1, C.k_out[l], C.bp[l], 1, C.ld_out[l]);
     LAUNCH_CHECK(h);
     if (C.Wt[l]) {
-      launch_k(t32::k_tf32_transpose, dim3((C.ld_in[l] + 31) / 32, (C.ld_out[l] + 31) / 32), dim3(32, 8), 0, st, C.Wp[l], C.ld_out[l],
-               C.ld_in[l], C.ld_in[l], C.Wt[l], C.ld_out[l]);
-      LAUNCH_CHECK(h);
+      int rc = tf32_split<0>(h, st, C.Wp[l], C.ld_in[l], C.ld_out[l], C.ld_in[l], C.Wsp_f[l]);
+      if (rc == MARF_OK) rc = tf32_split<1>(h, st, C.Wp[l], C.ld_in[l], C.ld_in[l], C.ld_out[l], C.Wt[l]);
+      if (rc) return rc;
     }
   }
   return MARF_OK;
@@ -482,8 +492,8 @@ static int chain_forward(marf_handle* h, cudaStream_t st, Chain& C, int M) {
       rc = out_forward(h, st, C, l, M);
     } else if (C.Wt[l] && tc_rows_ok(h, M)) {
       if (!last) C.bits_ok[l + 1] = C.bits[l + 1] != nullptr;
-      rc = last ? tgemm_nt<t32::T_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1], ldc, C.bp[l], 0)
-                : tgemm_nt<t32::T_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l], C.act[l + 1],
+      rc = last ? tgemm_nt<t32::T_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wsp_f[l], C.act[l + 1], ldc, C.bp[l], 0)
+                : tgemm_nt<t32::T_BIAS_RELU>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wsp_f[l], C.act[l + 1],
                                              ldc, C.bp[l], 0, C.bits[l + 1], C.bits_ld[l + 1]);
     } else
       rc = last ? sgemm<true, true, EPI_BIAS>(h, st, M, C.ld_out[l], C.ld_in[l], C.act[l], C.ld_in[l], C.Wp[l], C.ld_in[l],
@@ -535,7 +545,7 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
     }
     if (l == 0 && !C.need_dx0) break;
     if (l == 0) {
-      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wt[0], C.ld_out[0], nxt, C.ld_in[0], nullptr, 0)
+      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wt[0], nxt, C.ld_in[0], nullptr, 0)
                : sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[0], C.ld_out[0], cur, ldy, C.Wp[0], C.ld_in[0], nxt, C.ld_in[0],
                                                nullptr, 0, 1);
       if (rc) return rc;
@@ -545,7 +555,7 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
         LAUNCH_CHECK(h);
       }
     } else if (C.skip_mask & (1u << l)) {
-      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], h->dXscratch, C.ld_in[l], nullptr, 0)
+      rc = tcl ? tgemm_nt<t32::T_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], h->dXscratch, C.ld_in[l], nullptr, 0)
                : sgemm<true, false, EPI_PLAIN>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], h->dXscratch,
                                                C.ld_in[l], nullptr, 0, 1);
       if (rc) return rc;
@@ -559,9 +569,9 @@ static int chain_backward(marf_handle* h, cudaStream_t st, Chain& C, int M, floa
       LAUNCH_CHECK(h);
     } else {
       rc = tcl && C.bits_ok[l]
-               ? tgemm_nt<t32::T_RELU_BITS>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], nullptr, 0,
+               ? tgemm_nt<t32::T_RELU_BITS>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], nxt, C.ld_in[l], nullptr, 0,
                                             C.bits[l], C.bits_ld[l])
-           : tcl ? tgemm_nt<t32::T_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], C.ld_out[l], nxt, C.ld_in[l], C.act[l],
+           : tcl ? tgemm_nt<t32::T_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wt[l], nxt, C.ld_in[l], C.act[l],
                                             C.ld_in[l])
                : sgemm<true, false, EPI_RELU_MASK>(h, st, M, C.ld_in[l], C.ld_out[l], cur, ldy, C.Wp[l], C.ld_in[l], nxt,
                                                    C.ld_in[l], C.act[l], C.ld_in[l], 1);

@@ -16,8 +16,10 @@ struct Chain {                 // one MLP in padded fp32 workspace form
   float* gbp[MARF_MAX_LAYERS];
   float* act[MARF_MAX_LAYERS + 1];  // act[l]: input of layer l [chunk, ld_in[l]]; act[n]: logits [chunk, ld_out[n-1]]
   bool need_dx0 = false;       // image MLP: yes (warp gradient); mask head: no
-  // 3xTF32 tensor-core path (tc_tf32.cuh): W^T [ld_in, ld_out] for the dX layers, rebuilt by pack_chain every step;
-  // nullptr for layers that stay on k_sgemm (N or K < 32)
+  // 3xTF32 tensor-core path (tc_tf32.cuh): the weights split into big / small tf32 planes, [2 * pad16(N), pad32(K)], rebuilt by
+  // pack_chain every step: Wsp_f = W (forward: N = out, K = in), Wt = W^T (dX: N = in, K = out); nullptr for layers that stay
+  // on k_sgemm (N or K < 32)
+  float* Wsp_f[MARF_MAX_LAYERS] = {};
   float* Wt[MARF_MAX_LAYERS] = {};
   // sign bits of the input of layer l (= ReLU output of layer l - 1), [rows, bits_ld[l]] words, written by the tensor-core
   // forward layer and read by the dX layer instead of the fp32 input; bits_ok[l]: written by the last forward of this chunk

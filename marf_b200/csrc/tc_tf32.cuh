@@ -57,7 +57,8 @@ enum { MODE_NT = 0, MODE_TN = 1 };
 enum { T_BIAS = 0, T_BIAS_RELU = 1, T_PLAIN = 2, T_RELU_MASK = 3, T_RELU_BITS = 4 };
 
 struct Params {
-  // MODE_NT: C[M, 0..n_valid) = epi(A[M,K] * B[n_valid,K]^T);  A row-major [M, lda], B row-major [n_valid, ldb];
+  // MODE_NT: C[M, 0..n_valid) = epi(A[M,K] * B[n_valid,K]^T);  A row-major [M, lda]; B = the weights, split once per step into
+  //          big / small planes (k_tf32_split_w) and brought in by TMA (tmB);
   //          pair i works on the 256-row super-tiles i, i + pairs, ...; CTA r of the pair owns rows r*128.. of a super-tile
   //          and stages rows r*npad/2.. of B
   // MODE_TN: C[p, q] += sum_m A[m, p] * B[m, q];  A = P [M, lda], B = Q [M, ldb];  db[p] += sum_m P[m, p];
@@ -80,6 +81,9 @@ struct Params {
   int n_valid;           // MODE_NT: output columns (<= 256);  MODE_TN: columns of Q
   int p_valid;           // MODE_TN: columns of P
   int splits;            // MODE_TN: pairs along the rows
+  CUtensorMap tmB;       // MODE_NT: the split weights [2 x rows, K padded to 32] (big planes, then small planes from row b_small),
+                         //          box [bh rows x 32 columns], SWIZZLE_128B
+  int b_row0, b_small;   // MODE_NT: first row of this launch's column chunk; row offset of the small planes
   CUtensorMap tmC;       // MODE_NT: fp32 [M rows, n_valid columns] map of C, box [32 x 32], SWIZZLE_128B (TMA stores clip)
   CUtensorMap tmP, tmQ;  // MODE_TN: fp32 [M rows, valid columns] maps of P and Q, box [32 x 32], SWIZZLE_128B, zero fill
   long long* trace;      // diagnostics (MARF_T32_TRACE): clock64() stamps of CTA 0, [stage or tile][8]; nullptr in production
@@ -169,19 +173,22 @@ __device__ __forceinline__ void split_store4(uint32_t big, uint32_t small, const
   sts128(small, s);
 }
 
-// out[c][r] = in[r][c]  (the dX layers read W^T as a K-major operand)
-static __global__ void k_tf32_transpose(const float* __restrict__ in, int rows, int cols, int ld_in, float* __restrict__ out, int ld_out) {
+// Weights -> big / small tf32 planes, once per step:  out[n][k] = big(B[n][k]),  out[nr + n][k] = small(B[n][k]),  [2 nr, kpad]
+// row-major, zero outside (n < N, k < K).   TRANS = 0: B[n][k] = W[n * ldw + k] (forward: n = out, k = in);
+// TRANS = 1: B[n][k] = W[k * ldw + n] (dX: n = in, k = out)
+template <int TRANS>
+static __global__ void k_tf32_split_w(const float* __restrict__ W, int ldw, int N, int K, float* __restrict__ out, int nr, int kpad) {
   pdl_wait();
-  __shared__ float t[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < cols && r < rows) out[(size_t)c * ld_out + r] = t[threadIdx.x][i];
+  const int total = nr * kpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int n, k;
+    if (TRANS) { n = i % nr; k = i / nr; }      // consecutive threads read consecutive n (contiguous in W)
+    else       { k = i % kpad; n = i / kpad; }
+    float x = 0.f;
+    if (n < N && k < K) x = TRANS ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k];
+    const float big = tf32_rna(x);
+    out[(size_t)n * kpad + k] = big;
+    out[(size_t)(nr + n) * kpad + k] = tf32_rna(x - big);
   }
 }
 
@@ -201,7 +208,8 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
   uint64_t* acc_empty = acc_full + 2;       // [2]        leader CTA: 8 epilogue-warp arrivals
   uint64_t* raw_full = acc_empty + 2;       // [2]        MODE_TN: bytes of a raw stage landed
   uint64_t* raw_empty = raw_full + 2;       // [2]        MODE_TN: 8 loader warps have read the raw stage
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + 2);
+  uint64_t* full_b = raw_empty + 2;         // [kStages]  MODE_NT, leader CTA: the weight planes of both CTAs landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_b + kStages);
   constexpr int kSt = MODE == MODE_TN ? 2 : kStages;      // plane stages
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();            // 0 = leader (issues the MMAs)
@@ -230,7 +238,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
   const int pv = MODE == MODE_TN ? max(0, min(128, p.p_valid - p0)) : 128;       // valid accumulator rows of this CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 16); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 16); mbar_init(&empty[s], 1); mbar_init(&full_b[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 8); mbar_init(&raw_full[a], 1); mbar_init(&raw_empty[a], 8); }
     fence_barrier_init();
   }
@@ -255,6 +263,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
         for (int ks = 0; ks < st_count; ++ks, ++it) {
           const uint32_t s = it % kSt, ph = (it / kSt) & 1;
           mbar_wait_cluster(&full[s], ph);
+          if (MODE == MODE_NT) mbar_wait_cluster(&full_b[s], ph);
           tc_fence_after();
           if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && it < 512) p.trace[it * 8 + 4] = clock64();
           const uint32_t sa = smem_u32(smem + s * kStageBytes);
@@ -282,7 +291,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
     const int lw = lt >> 5;                   // loader warp 0..7
     // two register sets = the operands of two stages in flight: the loads of stage i + 2 are issued as soon as the registers
     // of stage i have been written to SMEM (they do not wait for an SMEM slot)
-    float4 va[8], vb[8];
+    float4 va[4], vb[4];
     const uint32_t full_remote = mapa_u32(smem_u32(&full[0]), 0);      // the leader's full[] barriers
     auto publish = [&](uint32_t s) {
       fence_proxy_async_smem();
@@ -290,53 +299,46 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
       if (lane == 0) mbar_arrive_cluster(full_remote + 8u * s);
     };
     if (MODE == MODE_NT) {
-      // chunk (row0 + 32 j, kc): row0 = lt >> 3 (0..31), kc = lt & 7; j = 0..3 for A (this CTA's 128 rows) and for B (this
-      // CTA's half of the operand rows); 8 lanes read one 128-byte row segment, SW128 offset of (row0 + 32 j, kc) = base + 4096 j
+      // A: chunk (row0 + 32 j, kc), row0 = lt >> 3 (0..31), kc = lt & 7, j = 0..3 (this CTA's 128 rows); 8 lanes read one
+      // 128-byte row segment, SW128 offset of (row0 + 32 j, kc) = base + 4096 j.  B (the pre-split weights): two TMA boxes per
+      // stage and CTA, issued by the first loader thread as soon as the slot is free.
       const int row0 = lt >> 3, kc = lt & 7;
       const uint32_t base = (uint32_t)(row0 >> 3) * 1024u + (uint32_t)(row0 & 7) * 128u + (uint32_t)((kc ^ (row0 & 7)) << 4);
-      const float* gB = p.B + (size_t)((int)rank * bh + row0) * p.ldb + kc * 4;
-      int nB = 0, nBs = 0;                    // B chunks inside the matrix (the rest is zero) / read by the MMA (rows < bh)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        nB += (row0 + 32 * j < bh && (int)rank * bh + row0 + 32 * j < nv) ? 1 : 0;
-        nBs += row0 + 32 * j < bh ? 1 : 0;
-      }
-      auto issue = [&](float4 (&v)[8], int i) {
+      auto issue = [&](float4 (&v)[4], int i) {
         if (i >= n_it) return;
         const int t = i / st_count, ks = i - t * st_count;
         const int row = ((pair + t * n_pairs) * 2 + (int)rank) * kTileM + row0;      // first of this thread's 4 rows of A
         const int k = ks * kStageK + kc * 4;
-        const bool kin = k < p.K;
-        const bool ain = kin && row < p.M;                 // (the last super-tile may have no second half)
+        const bool ain = k < p.K && row < p.M;             // (the last super-tile may have no second half)
         const float* gA = p.A + (size_t)row * p.lda + k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ain) v[j] = ldg128(gA + (size_t)(32 * j) * p.lda);
         }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kin && j < nB) v[4 + j] = ldg128(gB + (size_t)(32 * j) * p.ldb + ks * kStageK);
-        }
       };
-      auto stage = [&](float4 (&v)[8], int i) {
+      auto stage = [&](float4 (&v)[4], int i) {
         if (i >= n_it) return;
         const uint32_t s = (uint32_t)i % kStages, ph = ((uint32_t)i / kStages) & 1;
         mbar_wait_cluster(&empty[s], ph ^ 1);
+        if (lt == 0) {
+          const int ks = i % st_count;
+          uint8_t* sb = smem + s * kStageBytes + 2 * kPlane;
+          if (rank == 0) mbar_expect_tx(&full_b[s], 4u * (uint32_t)bh * 128u);
+          tma_load_2d_2sm(sb, &p.tmB, ks * kStageK, p.b_row0 + (int)rank * bh, &full_b[s], kEvictLast);
+          tma_load_2d_2sm(sb + kPlane, &p.tmB, ks * kStageK, p.b_small + p.b_row0 + (int)rank * bh, &full_b[s], kEvictLast);
+        }
         const bool tr = p.trace && blockIdx.x == 0 && lt == 0 && i < 512;
         if (tr) p.trace[i * 8 + 0] = clock64();
         const uint32_t sa = smem_u32(smem) + s * kStageBytes + base;
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_store4(sa + j * 4096, sa + kPlane + j * 4096, v[j]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nBs) split_store4(sa + 2 * kPlane + j * 4096, sa + 3 * kPlane + j * 4096, v[4 + j]);
         if (tr) p.trace[i * 8 + 1] = clock64();
         publish(s);
         if (tr) p.trace[i * 8 + 2] = clock64();
         issue(v, i + 2);
       };
+      if (lt == 0) prefetch_tmap(&p.tmB);
       issue(va, 0);
       issue(vb, 1);
       for (int i = 0; i < n_it; i += 2) {
