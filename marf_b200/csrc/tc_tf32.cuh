@@ -1,4 +1,4 @@
-// fp32-parity GEMMs on the tensor cores: 3xTF32 (sm_100a, tcgen05.mma kind::tf32).
+// fp32-parity GEMMs on the tensor cores: 3xTF32 (sm_100a, tcgen05.mma kind::tf32 on CTA pairs).
 //
 // Every fp32 operand x is split into  big = tf32(x)  and  small = tf32(x - big)  (round to nearest, 11 + 11 significant bits) and a
 // product is evaluated as  small_a*big_b + big_a*small_b + big_a*big_b  with fp32 accumulation in TMEM.  Measured against
@@ -10,23 +10,32 @@
 //   k_tf32x3<MODE_NT, EPI> : C[M,N] = epi(A[M,K] * B[N,K]^T)        forward layers (B = W) and dX layers (B = W^T)
 //   k_tf32x3<MODE_TN, *>   : C[N,K'] += P[M,N]^T * Q[M,K'] (+ db)    dW layers (contraction over the pixel rows), split over
 //                                                                    row ranges, red.add at the end
-// Operands stay plain row-major fp32 in global memory: 8 loader warps bring 16-byte chunks into registers, split them and
-// write both planes into the K-major SWIZZLE_128B layout the MMA reads (MODE_TN: transposing 4-byte scatter, lane mapping
-// chosen so that it is free of bank conflicts).  Splitting the weights in the kernel instead of streaming a pre-split image
-// halves the L2 -> SM bytes of a stage, which is what bounds the MODE_NT mainloop (every CTA re-reads the whole weight
-// matrix for every 128-row tile).
 //
-// The kernel runs on CTA pairs (clusters of 2, tcgen05 cta_group::2): one MMA is M = 256 (128 accumulator rows in each CTA's
-// TMEM) x N <= 256 with the B operand split across the pair (N/2 rows in each CTA's SMEM).  This is what makes the 3-term
-// product fit the SMEM bandwidth: a single-CTA M = 128 x N = 256 MMA re-reads 12 KB of SMEM per 128 cycles (96 of the 128
-// B/clk) and the loaders have to write another 96 KB per stage — measured 3,000 cycles per stage, 2x the MMA time; in the
-// pair each CTA reads 8 KB per MMA and writes 64 KB per stage, and the stages are small enough for a ring of three.
+// CTA pairs (clusters of 2, cta_group::2): one MMA is M = 256 (128 accumulator rows in each CTA's TMEM) x N <= 256 with the B
+// operand split across the pair (N/2 rows in each CTA's SMEM).  The shape follows from the SMEM pipe, which is what bounds a
+// 3-term product: a single-CTA M = 128 x N = 256 MMA re-reads 12 KB of operands per 128 cycles (96 of the 128 B/clk) while
+// the stage's 96 KB of planes have to be written — measured 3,000 cycles per stage, 2x the MMA time; in the pair a CTA reads
+// 8 KB per MMA, writes 64 KB per stage and has room for a ring of three stages.
+//
+// How the planes get into SMEM (history and measurements in profiles/r02_tf32_gemm.txt):
+//   weights (MODE_NT B):   split once per step (k_tf32_split_w), then 2 TMA boxes per stage and CTA (SWIZZLE_128B = the
+//                          K-major operand layout): no thread touches them
+//   activations (MODE_NT A): 8 loader warps, 16-byte chunks global -> registers (two register sets = two stages in flight)
+//                          -> two integer roundings (cvt.rna.tf32 issues at a quarter rate) -> st.shared.v4 of both planes
+//   MODE_TN (P and Q, both need a transposition: the contraction runs over rows): raw [32 x 128] tiles by TMA into a ring of
+//                          two raw stages, conflict-free ld.shared.v4, 4-byte scatter into the planes with a lane mapping
+//                          (16 rows x 2 chunks per warp) that hits 32 distinct banks; column sums of P (the bias gradient)
+//                          accumulate in registers on the way.  (Per-thread global loads of that shape are 16 x 32-byte
+//                          sectors per instruction and cost 4,100 cycles per stage; with TMA the kernel runs at the MMA rate.)
+//   epilogue (MODE_NT):    thread = accumulator row; bias / ReLU / sign bits / bit mask on the TMEM layout, [32 x 32] blocks
+//                          through a swizzled staging buffer and one TMA store each.  The forward layers leave one sign bit per
+//                          output (T_BIAS_RELU bits_out); the dX layers mask with those bits (T_RELU_BITS) instead of re-reading
+//                          the fp32 layer input (T_RELU_MASK, kept for inputs that did not come from a tensor-core layer).
 //
 // Warp roles, MODE_NT (416 threads): warp 0 = MMA issuer (leader CTA; + TMEM alloc), warps 1..8 = loaders, warps 9..12 =
 // epilogue (warp w owns TMEM lanes 32*(w%4)..+31); MODE_TN (384 threads): warps 0..7 = loaders, warps 8..11 = epilogue, lane
-// 0 of warp 8 issues the MMAs first.  Three SMEM stages of 32 K-elements (A and B-half: 2 planes x 16 KB each), two TMEM
-// accumulators of 256 columns, one 4 KB staging block per epilogue warp (the accumulator rows are re-read transposed so that
-// global stores / mask loads are whole 128-byte lines).
+// 0 of warp 8 issues the MMAs first and lane 0 of warp 9 the TMA loads.  SMEM stages of 32 K-elements (A and B-half: 2
+// planes x 16 KB each), two TMEM accumulators of 256 columns.
 #pragma once
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -125,14 +134,6 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t desc_a, 
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
