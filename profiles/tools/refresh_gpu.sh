@@ -11,4 +11,6 @@ $C2 > gpurun_out/plain_c2.log 2>&1 && ncu --kernel-name regex:k_ --metrics $M --
 C4="python bench.py --workload config4 --steps 1 --warmup 3 --no-cpu --headline-only"
 $C4 > gpurun_out/plain_c4.log 2>&1 && ncu --kernel-name regex:k_ --metrics $M --clock-control none -s 1400 -c 120 --csv --log-file gpurun_out/launches_r02_config4.csv $C4 > gpurun_out/ncu_c4.log 2>&1
 $C2 > gpurun_out/plain_c2b.log 2>&1 && ncu --set full --import-source on --clock-control none --kernel-name regex:"k_tc_bwd|k_tc_chain" --launch-skip 8 --launch-count 2 -o gpurun_out/r02_top_kernels $C2 > gpurun_out/ncu_full.log 2>&1
+F2="python bench.py --precision fp32 --workload config2 --steps 2 --warmup 3 --no-cpu --headline-only"
+$F2 > gpurun_out/plain_f2.log 2>&1 && ncu --kernel-name regex:k_ --metrics $M --clock-control none --launch-skip 700 -c 340 --csv --log-file gpurun_out/launches_r02_fp32_config2.csv $F2 > gpurun_out/ncu_f2.log 2>&1
 tail -c 400 gpurun_out/bench_r02_final.json

@@ -53,6 +53,31 @@ for cfg in ("config2", "config4"):
         for key, nice in names.items():
             if key in n:
                 traffic[cfg][nice] = int(v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0))
+# precision=fp32, config 2: one step between two k_sl3_backward launches
+src = os.path.join(G, "launches_r02_fp32_config2.csv")
+if os.path.exists(src):
+    shutil.copy(src, os.path.join(P, "r02_launches_fp32_config2.csv"))
+    L = launches(src)
+    st = [i for i, (n, _) in enumerate(L) if "k_sl3_backward" in n]
+    seg = L[st[-2] + 1:st[-1] + 1]
+    agg = collections.OrderedDict()
+    for n, v in seg:                      # (one line per kernel: ~100 launches per step)
+        a = agg.setdefault(n, collections.Counter())
+        a["launches"] += 1
+        for k, x in v.items():
+            a[k] += x
+    rows_ = sorted(agg.items(), key=lambda kv: -kv[1]["gpu__time_duration.sum"])
+    tot = sum(a["gpu__time_duration.sum"] for _, a in rows_) / 1e3
+    out = ["# one training step of config 2 (216,000 px-samples, image MLP + mask head + edge term), precision=fp32 (3xTF32 tensor-core GEMMs), "
+           "summed per kernel; ncu --clock-control none (cold-cache, serialised: compare shares)", "kernel,launches,us,share_pct,dram_read_MB,dram_write_MB,tensor_pipe_pct(avg)"]
+    for n, a in rows_:
+        us = a["gpu__time_duration.sum"] / 1e3
+        out.append(f'{n},{a["launches"]},{us:.1f},{100 * us / tot:.1f},{a["dram__bytes_read.sum"] / 1e6:.1f},{a["dram__bytes_write.sum"] / 1e6:.1f},'
+                   f'{a["sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active"] / a["launches"]:.1f}')
+    out.append(f"TOTAL,{len(seg)},{tot:.1f},100,,,")
+    open(os.path.join(P, "r02_step_kernels_fp32_config2.csv"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
 for cfg, t in traffic.items():
     json.dump({"workload": cfg, "precision": "bf16",
                "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, one launch of each kernel inside a training step (profiles/r02_step_kernels_{cfg}.csv)",
