@@ -454,31 +454,31 @@ static int pick_split(int M, int N, int K) {
 
 static int pack_chain(marf_handle* h, cudaStream_t st, Chain& C, const float* const* W, const float* const* b) {
   if (!W || !b) return fail(h, MARF_ERR_INVALID, "missing parameter pointers");
+  ChainPackJobs J{};
+  int biggest = 0;
   for (int l = 0; l < C.n; ++l) {
     if (!W[l] || !b[l]) return fail(h, MARF_ERR_INVALID, "null layer parameter");
-    int tot = C.ld_out[l] * C.ld_in[l];
-    launch_k(k_pack, (tot + 255) / 256, 256, 0, st, W[l], C.k_out[l], C.k_in[l], C.Wp[l], C.ld_out[l], C.ld_in[l]);
-    LAUNCH_CHECK(h);
-    launch_k(k_pack, (C.ld_out[l] + 255) / 256, 256, 0, st, b[l], 1, C.k_out[l], C.bp[l], 1, C.ld_out[l]);
-    LAUNCH_CHECK(h);
-    if (C.Wt[l]) {
-      int rc = tf32_split<0>(h, st, C.Wp[l], C.ld_in[l], C.ld_out[l], C.ld_in[l], C.Wsp_f[l]);
-      if (rc == MARF_OK) rc = tf32_split<1>(h, st, C.Wp[l], C.ld_in[l], C.ld_in[l], C.ld_out[l], C.Wt[l]);
-      if (rc) return rc;
-    }
+    J.W[l] = W[l]; J.b[l] = b[l]; J.Wp[l] = C.Wp[l]; J.bp[l] = C.bp[l];
+    J.sp_f[l] = C.Wt[l] ? C.Wsp_f[l] : nullptr;
+    J.sp_t[l] = C.Wt[l];
+    J.k_out[l] = C.k_out[l]; J.k_in[l] = C.k_in[l]; J.ld_out[l] = C.ld_out[l]; J.ld_in[l] = C.ld_in[l];
+    biggest = std::max(biggest, (int)round_up(C.ld_out[l], 16) * (int)round_up(C.ld_in[l], 32));
   }
+  launch_k(k_pack_chain, dim3(std::max(1, std::min(64, (biggest + 1023) / 1024)), C.n), 256, 0, st, J);
+  LAUNCH_CHECK(h);
   return MARF_OK;
 }
-
 static int unpack_chain(marf_handle* h, cudaStream_t st, Chain& C, float* const* gW, float* const* gb) {
   if (!gW || !gb) return fail(h, MARF_ERR_INVALID, "missing gradient pointers");
+  ChainUnpackJobs J{};
+  int biggest = 0;
   for (int l = 0; l < C.n; ++l) {
-    int tot = C.k_out[l] * C.k_in[l];
-    launch_k(k_unpack, (tot + 255) / 256, 256, 0, st, C.gWp[l], C.ld_in[l], gW[l], C.k_out[l], C.k_in[l]);
-    LAUNCH_CHECK(h);
-    launch_k(k_unpack, (C.k_out[l] + 255) / 256, 256, 0, st, C.gbp[l], C.ld_out[l], gb[l], 1, C.k_out[l]);
-    LAUNCH_CHECK(h);
+    J.gWp[l] = C.gWp[l]; J.gbp[l] = C.gbp[l]; J.gW[l] = gW[l]; J.gb[l] = gb[l];
+    J.k_out[l] = C.k_out[l]; J.k_in[l] = C.k_in[l]; J.ld_in[l] = C.ld_in[l];
+    biggest = std::max(biggest, C.k_out[l] * C.k_in[l]);
   }
+  launch_k(k_unpack_chain, dim3(std::max(1, std::min(64, (biggest + 1023) / 1024)), C.n), 256, 0, st, J);
+  LAUNCH_CHECK(h);
   return MARF_OK;
 }
 

@@ -509,6 +509,71 @@ static __global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* _
   int r = i / cols, c = i - r * cols;
   W[i] = Wp[(size_t)r * pcol + c];
 }
+// Whole-chain weight pack / gradient unpack in ONE launch each (blockIdx.y = layer): torch layouts <-> the zero-padded
+// workspace, plus (3xTF32 path) the big / small tf32 planes of W and of W^T that the tensor-core layers read by TMA.
+struct ChainPackJobs {
+  const float* W[MARF_MAX_LAYERS];     // [k_out, k_in] torch layout
+  const float* b[MARF_MAX_LAYERS];
+  float* Wp[MARF_MAX_LAYERS];          // [ld_out, ld_in]
+  float* bp[MARF_MAX_LAYERS];          // [ld_out]
+  float* sp_f[MARF_MAX_LAYERS];        // [2 * pad16(ld_out), pad32(ld_in)]  (nullptr: layer stays on the CUDA cores)
+  float* sp_t[MARF_MAX_LAYERS];        // [2 * pad16(ld_in), pad32(ld_out)]
+  int k_out[MARF_MAX_LAYERS], k_in[MARF_MAX_LAYERS], ld_out[MARF_MAX_LAYERS], ld_in[MARF_MAX_LAYERS];
+};
+__device__ __forceinline__ float tf32_round_bits(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+static __global__ void k_pack_chain(const __grid_constant__ ChainPackJobs J) {
+  pdl_wait();
+  const int l = blockIdx.y;
+  const float* __restrict__ W = J.W[l];
+  const int ko = J.k_out[l], ki = J.k_in[l], lo = J.ld_out[l], li = J.ld_in[l];
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < lo * li; i += stride) {
+    const int r = i / li, c = i - r * li;
+    J.Wp[l][i] = (r < ko && c < ki) ? W[(size_t)r * ki + c] : 0.f;
+  }
+  for (int i = t0; i < lo; i += stride) J.bp[l][i] = i < ko ? J.b[l][i] : 0.f;
+  if (J.sp_f[l]) {
+    {   // forward operand: B[n = out][k = in]
+      const int nr = (lo + 15) / 16 * 16, kp = (li + 31) / 32 * 32;
+      for (int i = t0; i < nr * kp; i += stride) {
+        const int n = i / kp, k = i - n * kp;
+        const float x = (n < ko && k < ki) ? W[(size_t)n * ki + k] : 0.f;
+        const float big = tf32_round_bits(x);
+        J.sp_f[l][i] = big;
+        J.sp_f[l][(size_t)nr * kp + i] = tf32_round_bits(x - big);
+      }
+    }
+    {   // dX operand: B[n = in][k = out] = W[k][n]; consecutive threads take consecutive n (contiguous in W)
+      const int nr = (li + 15) / 16 * 16, kp = (lo + 31) / 32 * 32;
+      for (int i = t0; i < nr * kp; i += stride) {
+        const int k = i / nr, n = i - k * nr;
+        const float x = (n < ki && k < ko) ? W[(size_t)k * ki + n] : 0.f;
+        const float big = tf32_round_bits(x);
+        J.sp_t[l][(size_t)n * kp + k] = big;
+        J.sp_t[l][(size_t)(nr + n) * kp + k] = tf32_round_bits(x - big);
+      }
+    }
+  }
+}
+struct ChainUnpackJobs {
+  const float* gWp[MARF_MAX_LAYERS];
+  const float* gbp[MARF_MAX_LAYERS];
+  float* gW[MARF_MAX_LAYERS];
+  float* gb[MARF_MAX_LAYERS];
+  int k_out[MARF_MAX_LAYERS], k_in[MARF_MAX_LAYERS], ld_in[MARF_MAX_LAYERS];
+};
+static __global__ void k_unpack_chain(const __grid_constant__ ChainUnpackJobs J) {
+  pdl_wait();
+  const int l = blockIdx.y;
+  const int ko = J.k_out[l], ki = J.k_in[l], li = J.ld_in[l];
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int i = t0; i < ko * ki; i += stride) {
+    const int r = i / ki, c = i - r * ki;
+    J.gW[l][i] = J.gWp[l][(size_t)r * li + c];
+  }
+  for (int i = t0; i < ko; i += stride) J.gb[l][i] = J.gbp[l][i];
+}
+
 // copy `cols` columns between row-major buffers (skip-connection concat / split)
 static __global__ void k_copy_cols(int M, int cols, const float* __restrict__ src, int lds, int soff, float* __restrict__ dst,
                             int ldd, int doff, int accumulate) {
@@ -602,8 +667,25 @@ static __global__ void __launch_bounds__(256) k_out_backward(int M, int K, int n
     for (int i = 0; i < KCH; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) aw[j][i][e] = 0.f;
-  for (int m = blockIdx.x * 8 + warp; m < M; m += nwarps) {
-    const float4 d4 = *reinterpret_cast<const float4*>(dY + (size_t)m * ldy);      // (ldy = 4: the padded logits row)
+  // the next row's operands are requested while the current row is processed (one 1 KB row per warp and iteration would
+  // leave the loads latency-bound)
+  float4 xn[KCH], dn = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_row = [&](int m) {
+    dn = *reinterpret_cast<const float4*>(dY + (size_t)m * ldy);      // (ldy = 4: the padded logits row)
+#pragma unroll
+    for (int i = 0; i < KCH; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      xn[i] = c < K ? *reinterpret_cast<const float4*>(X + (size_t)m * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int m = blockIdx.x * 8 + warp;
+  if (m < M) load_row(m);
+  for (; m < M; m += nwarps) {
+    const float4 d4 = dn;
+    float4 xc[KCH];
+#pragma unroll
+    for (int i = 0; i < KCH; ++i) xc[i] = xn[i];
+    if (m + nwarps < M) load_row(m + nwarps);
     const float d[4] = {d4.x, n_out > 1 ? d4.y : 0.f, n_out > 2 ? d4.z : 0.f, n_out > 3 ? d4.w : 0.f};
 #pragma unroll
     for (int j = 0; j < 4; ++j) ab[j] += d[j];
@@ -611,8 +693,7 @@ static __global__ void __launch_bounds__(256) k_out_backward(int M, int K, int n
     for (int i = 0; i < KCH; ++i) {
       const int c = (lane + 32 * i) * 4;
       if (c < K) {
-        const float4 x = *reinterpret_cast<const float4*>(X + (size_t)m * ldx + c);
-        const float xv[4] = {x.x, x.y, x.z, x.w};
+        const float xv[4] = {xc[i].x, xc[i].y, xc[i].z, xc[i].w};
         float g[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
