@@ -321,10 +321,10 @@ template <int EPI>
 static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const float* A, int lda, const float* Bsp, float* C,
                     int ldc, const float* aux, int ldaux, uint32_t* bits = nullptr, int bits_ld = 0) {
   const int nr = (int)round_up(N, 16), kpad = (int)round_up(K, 32);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};               // (the attribute is per device)
+  if (!attr_set[h->cfg.device & 63]) {
     CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, t32::kSmemBytes));
-    attr_set = true;
+    attr_set[h->cfg.device & 63] = true;
   }
   for (int n0 = 0; n0 < N; n0 += 256) {
     t32::Params p{};
@@ -353,11 +353,11 @@ static int tgemm_nt(marf_handle* h, cudaStream_t st, int M, int N, int K, const 
 // C[Np, Nq] += P[M, Np]^T * Q[M, Nq];  db[Np] += column sums of P (optional)
 static int tgemm_tn(marf_handle* h, cudaStream_t st, int M, int Np, int Nq, const float* P, int ldp, const float* Q, int ldq, float* C,
                     int ldc, float* db) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};               // (the attribute is per device)
+  if (!attr_set[h->cfg.device & 63]) {
     CUDA_TRY(h, cudaFuncSetAttribute(t32::k_tf32x3<t32::MODE_TN, t32::T_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      t32::kSmemBytes));
-    attr_set = true;
+    attr_set[h->cfg.device & 63] = true;
   }
   t32::Params p{};
   p.A = P; p.lda = ldp; p.B = Q; p.ldb = ldq;

@@ -494,21 +494,6 @@ static __global__ void k_colsum(int M, int N, const float* __restrict__ dY, int 
   }
 }
 
-// weight (un)packing between torch layouts and the padded workspace
-static __global__ void k_pack(const float* __restrict__ W, int rows, int cols, float* __restrict__ Wp, int prow, int pcol) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= prow * pcol) return;
-  int r = i / pcol, c = i - r * pcol;
-  Wp[i] = (r < rows && c < cols) ? W[(size_t)r * cols + c] : 0.f;
-}
-static __global__ void k_unpack(const float* __restrict__ Wp, int pcol, float* __restrict__ W, int rows, int cols) {
-  pdl_wait();
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * cols) return;
-  int r = i / cols, c = i - r * cols;
-  W[i] = Wp[(size_t)r * pcol + c];
-}
 // Whole-chain weight pack / gradient unpack in ONE launch each (blockIdx.y = layer): torch layouts <-> the zero-padded
 // workspace, plus (3xTF32 path) the big / small tf32 planes of W and of W^T that the tensor-core layers read by TMA.
 struct ChainPackJobs {

@@ -128,6 +128,28 @@ def test_fp32_tensor_core_and_cuda_core_paths_agree(monkeypatch):
         cases.check_close(out["1"]["grads"][k], v, 2e-4, k)
 
 
+@pytest.mark.parametrize("name", ["mid_mask_c2f", "implicit_edges"])
+def test_step_fp32_is_graph_capturable(name):
+    """include/marf_b200.h: no entry point of the step synchronises — one fp32 marf_step (3xTF32 GEMMs: tensor maps are
+    encoded on the host per launch and travel as kernel parameters) can be captured into a CUDA graph and replayed."""
+    import gpu_util
+    cfg, params, images, it, progress, g = cases.build_case(name)
+    eng = gpu_util.make_engine(cfg, "fp32")
+    ref = gpu_util.run_step(eng, cfg, params, images, it, progress)      # (also warms the data caches and loads the kernels)
+    kw = gpu_util.step_kwargs(eng, cfg, params, images, it, progress)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        eng.step(**kw)
+    for t in kw["g_mlp_w"] + [kw["g_warp"]]:
+        t.fill_(7.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    for got, want in ((kw["g_warp"].cpu(), ref["grads"]["gwarp"]), (kw["g_mlp_w"][1].cpu(), ref["grads"]["gW1"])):
+        assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["small_mask_c2f", "mid_mask", "implicit"])
 def test_step_fp32_chunked(name):
     """several passes over the pixel range (recompute-forward backward) must not change the result."""
