@@ -644,7 +644,7 @@ static int forward_chunk(marf_handle* h, const marf_step_io* io, cudaStream_t st
   if (rc) return rc;
   if (h->cfg.mask_mode == MARF_MASK_IMPLICIT) {
     if (!(h->feats_valid && h->n_chunks == 1)) {
-      launch_k(k_mask_features, rg.padded, 128, 0, st, h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_n_vocab,
+      launch_k(k_mask_features, std::min((rg.padded + 7) / 8, 16 * h->n_sms), 256, 0, st, h->geo, rg, io->rgb, io->embed, h->cfg.mask_embed_dim, h->cfg.mask_n_vocab,
                h->cfg.mask_uv_freqs, h->msk.act[0], h->msk.ld_in[0], h->bad_index);
       LAUNCH_CHECK(h);
       h->feats_valid = h->n_chunks == 1;

@@ -314,48 +314,56 @@ static __global__ void k_encode_backward(Geo g, PxRange rg, const float* __restr
 
 // ============================================================================================
 // mask-head input features (model/planar.py:342-349, :491-518): [E[trunc r], E[trunc g], E[trunc b], PosEmbedding(xy)]
-// one block of 128 threads per pixel-sample row; iteration-invariant (cached by the engine when possible).
+// one warp per pixel-sample row (8 rows per block, grid-stride), 16-byte copies of the embedding rows; iteration-invariant
+// (cached by the engine when possible).
 // ============================================================================================
-static __global__ void k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
+static __global__ void __launch_bounds__(256) k_mask_features(Geo g, PxRange rg, const float* __restrict__ rgb, const float* __restrict__ embed,
                                 int embed_dim, int n_vocab, int n_freqs, float* __restrict__ F, int ld, double* __restrict__ bad) {
   pdl_wait();
-  int t = blockIdx.x;
-  float* o = F + (size_t)t * ld;
-  if (t >= rg.count) {
-    for (int j = threadIdx.x; j < ld; j += blockDim.x) o[j] = 0.0f;
-    return;
-  }
-  int b, r, c;
-  long long i = rg.first + t;
-  decode_px(g, i, b, r, c);
-  long long per = (long long)g.rows * g.w;
-  long long rem = i - (long long)b * per;
-  int k_col = 3 * embed_dim;
-  for (int j = threadIdx.x; j < k_col; j += blockDim.x) {
-    int ch = j / embed_dim, e = j - ch * embed_dim;
-    float val = rgb[((long long)b * 3 + ch) * per + rem];
-    long long idx = (long long)val;                 // .long(): truncation toward zero
-    if (idx < 0 || idx >= n_vocab) {                // the reference raises IndexError here (nn.Embedding, model/planar.py:344)
-      if (e == 0) atomicAdd(bad, 1.0);
-      idx = idx < 0 ? 0 : n_vocab - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long per = (long long)g.rows * g.w;
+  const int k_col = 3 * embed_dim, k_uv = 2 + 4 * n_freqs;
+  const bool vec = (embed_dim & 3) == 0 && (ld & 3) == 0;
+  for (int t = blockIdx.x * 8 + warp; t < rg.padded; t += gridDim.x * 8) {
+    float* o = F + (size_t)t * ld;
+    if (t >= rg.count) {
+      for (int j = lane; j < ld; j += 32) o[j] = 0.0f;
+      continue;
     }
-    o[j] = embed[idx * embed_dim + e];
-  }
-  float x, y;
-  grid_xy(g, r, c, x, y);
-  int k_uv = 2 + 4 * n_freqs;
-  for (int j = threadIdx.x; j < k_uv; j += blockDim.x) {
-    float val;
-    if (j < 2) val = j == 0 ? x : y;
-    else {
-      int q = j - 2, fi = q / 4, w4 = q % 4;        // per frequency: sin x, sin y, cos x, cos y
-      float f = (float)(1 << fi);
-      float a = f * ((w4 & 1) ? y : x);
-      val = (w4 < 2) ? sinf(a) : cosf(a);
+    int b, r, c;
+    const long long i = rg.first + t;
+    decode_px(g, i, b, r, c);
+    const long long rem = i - (long long)b * per;
+    for (int ch = 0; ch < 3; ++ch) {
+      const float val = rgb[((long long)b * 3 + ch) * per + rem];
+      long long idx = (long long)val;                 // .long(): truncation toward zero
+      if (idx < 0 || idx >= n_vocab) {                // the reference raises IndexError here (nn.Embedding, model/planar.py:344)
+        if (lane == 0) atomicAdd(bad, 1.0);
+        idx = idx < 0 ? 0 : n_vocab - 1;
+      }
+      const float* e = embed + idx * embed_dim;
+      float* oc = o + ch * embed_dim;
+      if (vec) {
+        for (int j = lane * 4; j < embed_dim; j += 128) *reinterpret_cast<float4*>(oc + j) = *reinterpret_cast<const float4*>(e + j);
+      } else {
+        for (int j = lane; j < embed_dim; j += 32) oc[j] = e[j];
+      }
     }
-    o[k_col + j] = val;
+    float x, y;
+    grid_xy(g, r, c, x, y);
+    for (int j = lane; j < k_uv; j += 32) {
+      float val;
+      if (j < 2) val = j == 0 ? x : y;
+      else {
+        const int q = j - 2, fi = q >> 2, w4 = q & 3;  // per frequency: sin x, sin y, cos x, cos y
+        const float f = (float)(1 << fi);
+        const float a = f * ((w4 & 1) ? y : x);
+        val = (w4 < 2) ? sinf(a) : cosf(a);
+      }
+      o[k_col + j] = val;
+    }
+    for (int j = k_col + k_uv + lane; j < ld; j += 32) o[j] = 0.0f;
   }
-  for (int j = k_col + k_uv + threadIdx.x; j < ld; j += blockDim.x) o[j] = 0.0f;
 }
 
 // ============================================================================================
