@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
     const int q = warp & 3;
     const uint32_t stg = smem_u32(sOut) + q * 4096;   // this warp's [32 rows x 32 columns] staging block, 16-byte chunks swizzled by row
     if ((EPI == T_BIAS || EPI == T_BIAS_RELU) && MODE == MODE_NT) {
-      for (int i = threadIdx.x - 32 * kEpiWarp0; i < 256; i += 128) sBias[i] = i < nv ? p.aux[i] : 0.f;
+      for (int i = threadIdx.x - 32 * kEpiWarp0; i < 256; i += 128) sts32(smem_u32(sBias) + 4u * i, i < nv ? p.aux[i] : 0.f);
       named_bar_sync(1, 128);
     }
     const uint32_t acc_empty_remote = mapa_u32(smem_u32(&acc_empty[0]), 0);
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
             float4 y = make_float4(__uint_as_float(v[c4 * 4]), __uint_as_float(v[c4 * 4 + 1]), __uint_as_float(v[c4 * 4 + 2]),
                                    __uint_as_float(v[c4 * 4 + 3]));
             if (EPI == T_BIAS || EPI == T_BIAS_RELU) {
-              const float4 b = *reinterpret_cast<const float4*>(sBias + g * 32 + c4 * 4);
+              const float4 b = lds128(smem_u32(sBias) + 4u * (g * 32 + c4 * 4));
               y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
               if (EPI == T_BIAS_RELU) {
                 y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f);
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(MODE == MODE_TN ? kThreadsTN : kThreads, 1) k_
             if (MODE == MODE_NT) {
               const size_t grow = (size_t)(tile_row0(t) + q * 32 + row);
               if (EPI == T_BIAS || EPI == T_BIAS_RELU) {
-                const float4 b = *reinterpret_cast<const float4*>(sBias + col);
+                const float4 b = lds128(smem_u32(sBias) + 4u * col);
                 y.x += b.x; y.y += b.y; y.z += b.z; y.w += b.w;
                 if (EPI == T_BIAS_RELU) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
                 if (EPI == T_BIAS_RELU && p.bits_out) obits[i] = (y.x > 0.f ? 1u : 0u) | (y.y > 0.f ? 2u : 0u) | (y.z > 0.f ? 4u : 0u) | (y.w > 0.f ? 8u : 0u);

@@ -175,6 +175,34 @@ def test_no_predicated_tensor_core_mma_in_sass():
     assert not bad, bad[:4]
 
 
+def test_fp32_mode_kernels_are_tensor_core_kernels_in_sass():
+    """precision=fp32 runs its wide layers as 3xTF32 GEMMs (csrc/tc_tf32.cuh): the built k_tf32x3 kernels must hold CTA-pair
+    tensor-core MMAs, TMA loads / stores and TMEM loads, and must address shared memory with STS / LDS (through the rounded-up
+    dynamic-SMEM pointer the compiler once emitted generic ST.E / LD.E for every operand plane: 2-3x the loaders' issue time)."""
+    import collections
+    import re
+    import shutil
+    import subprocess
+    from marf_b200 import build
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    sass = subprocess.run([cuobjdump, "-sass", build.build()], capture_output=True, text=True, check=True).stdout
+    ops, fn, n_fn = collections.Counter(), None, 0
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+            n_fn += "k_tf32x3" in fn
+            continue
+        if fn and "k_tf32x3" in fn:
+            m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][\w.]*)", line)
+            if m:
+                ops[m.group(1).split(".")[0] + ("." + m.group(1).split(".")[1] if m.group(1).startswith(("ST.", "LD.")) else "")] += 1
+    assert n_fn == 6, n_fn                      # NT x {bias, bias+relu, plain, relu-mask, relu-bits} + TN
+    for need in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STS", "LDS"):
+        assert ops[need] > 0, (need, dict(ops))
+    assert ops["ST.E"] == 0, "generic stores in the 3xTF32 kernels (shared-memory planes must be written with st.shared)"
+
+
 def test_bench_roofline_arithmetic():
     """bench.roofline_lines: algorithmic FLOP / bytes per kernel class, the dominant kernel against the TENSOR roofline
      with the HBM view and the traffic ratio beside it."""
